@@ -1,0 +1,530 @@
+// librtfs_b200.so -- C ABI + launch orchestration of the RTFS-Net forward path (see
+// include/rtfs_b200.h for the contract and the reference file:line each entry point replaces).
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/rtfs_b200.h"
+#include "attention.cuh"
+#include "caf.cuh"
+#include "dprnn.cuh"
+#include "dwconv.cuh"
+#include "frontend.cuh"
+#include "gemm.cuh"
+
+using namespace rtfs;
+
+namespace {
+
+thread_local std::string g_err;
+thread_local long long g_launches = 0;
+
+struct Dims {
+    int B, T, F, Tc, Fc, Tv;
+    long long P, Pc;
+};
+
+Dims make_dims(int B, int T, int Tv) {
+    Dims d;
+    d.B = B;
+    d.T = T;
+    d.F = RTFS_F;
+    d.Tc = (T - 2) / 2 + 1;
+    d.Fc = RTFS_FC;
+    d.Tv = Tv;
+    d.P = (long long)T * d.F;
+    d.Pc = (long long)d.Tc * d.Fc;
+    return d;
+}
+
+struct Plan {
+    long long off[RTFS_WS_COUNT];
+    long long total;
+};
+
+Plan make_plan(const Dims& d) {
+    const long long B = d.B;
+    const long long A = B * d.P * 256, H = B * d.P * 64, G = B * d.Pc * 64;
+    long long sz[RTFS_WS_COUNT];
+    for (int i = 0; i < RTFS_WS_COUNT; ++i) sz[i] = G;
+    sz[RTFS_WS_SPEC] = B * d.P * 2;
+    sz[RTFS_WS_A0] = sz[RTFS_WS_A1] = sz[RTFS_WS_XA] = sz[RTFS_WS_XB] = A;
+    sz[RTFS_WS_P_PRE] = sz[RTFS_WS_D0_PRE] = sz[RTFS_WS_LE0_PRE] = sz[RTFS_WS_LEC_PRE] = H;
+    sz[RTFS_WS_N] = sz[RTFS_WS_HA] = sz[RTFS_WS_HB] = G + 8 * 64;
+    const long long hp_f = (long long)d.Tc * (d.Fc + 7), hp_t = (long long)d.Fc * (d.Tc + 7);
+    sz[RTFS_WS_HPAD] = B * (hp_f > hp_t ? hp_f : hp_t) * 64 + 8 * 64;
+    sz[RTFS_WS_U] = B * d.Pc * 256 + 8 * 256;
+    sz[RTFS_WS_Q] = sz[RTFS_WS_K] = B * d.Pc * 16;
+    sz[RTFS_WS_Q18] = B * d.P * 18;
+    sz[RTFS_WS_STATS] = (long long)RTFS_ST_COUNT * B * 2 * 2;  // doubles, counted in floats
+    sz[RTFS_WS_VK] = sz[RTFS_WS_ATT] = B * (long long)(d.Tv > 0 ? d.Tv : 1) * 256;
+    Plan p;
+    long long o = 0;
+    for (int i = 0; i < RTFS_WS_COUNT; ++i) {
+        p.off[i] = o;
+        o += ((sz[i] * 4 + 255) / 256) * 256;
+    }
+    p.total = o;
+    return p;
+}
+
+struct Ctx {
+    const float* const* P;
+    Dims d;
+    Plan pl;
+    char* ws;
+    cudaStream_t st;
+    float* buf(int i) const { return reinterpret_cast<float*>(ws + pl.off[i]); }
+    double* stat(int slot) const { return reinterpret_cast<double*>(ws + pl.off[RTFS_WS_STATS]) + (long long)slot * d.B * 2; }
+    GlnRef gln(int slot, int pg, int pb, long long n) const {
+        GlnRef r;
+        r.sums = stat(slot);
+        r.gamma = P[pg];
+        r.beta = P[pb];
+        r.inv_n = 1.0 / (double)n;
+        return r;
+    }
+};
+
+int fail(const char* what, cudaError_t e) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return -1;
+}
+int fail_msg(const std::string& m) {
+    g_err = m;
+    return -2;
+}
+
+#define CK(call)                                   \
+    do {                                           \
+        cudaError_t e__ = (call);                  \
+        ++g_launches;                              \
+        if (e__ != cudaSuccess) return fail(#call, e__); \
+    } while (0)
+#define RUN(call)                 \
+    do {                          \
+        int r__ = (call);         \
+        if (r__ != 0) return r__; \
+    } while (0)
+
+// ------------------------------------------------------------------ generic gLN statistics (module-level calls only)
+__global__ void __launch_bounds__(256) gln_stats_kernel(const float* __restrict__ x, long long n_per_sample, double* sums) {
+    __shared__ float scratch[16];
+    const int b = blockIdx.y;
+    const float4* p = reinterpret_cast<const float4*>(x + (long long)b * n_per_sample);
+    const long long n4 = n_per_sample / 4;
+    float s = 0.f, q = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(p + i);
+        s += v.x + v.y + v.z + v.w;
+        q += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    block_stats_atomic(s, q, sums + 2 * b, scratch);
+}
+
+// ------------------------------------------------------------------ stages
+int run_encoder(const Ctx& c, const float* wav, float* a0, int L) {
+    const Dims& d = c.d;
+    StftArgs sa{wav, c.P[RTFS_P_WINDOW], c.P[RTFS_P_COSTAB], c.P[RTFS_P_SINTAB], c.buf(RTFS_WS_SPEC), L, d.T};
+    stft_kernel<<<dim3(d.T, d.B), 288, 0, c.st>>>(sa);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(c.stat(RTFS_ST_A0), 0, sizeof(double) * 2 * d.B, c.st));
+    Im2colLoader al{c.buf(RTFS_WS_SPEC), d.T, d.F};
+    StatsEpi ep{a0, 256, nullptr, c.stat(RTFS_ST_A0), (int)d.P, d.B};
+    CK((launch_gemm<128, 32, true>(al, c.P[RTFS_P_ENC_W], ep, (int)(d.B * d.P), 256, c.st)));
+    return 0;
+}
+
+int run_bottleneck(const Ctx& c, const float* a0, float* a1, bool compute_stats) {
+    const Dims& d = c.d;
+    if (compute_stats) {
+        CK(cudaMemsetAsync(c.stat(RTFS_ST_A0), 0, sizeof(double) * 2 * d.B, c.st));
+        gln_stats_kernel<<<dim3(64, d.B), 256, 0, c.st>>>(a0, d.P * 256, c.stat(RTFS_ST_A0));
+        CK(cudaGetLastError());
+    }
+    GlnActLoader<256, 1> al{a0, c.gln(RTFS_ST_A0, RTFS_P_BN_GAMMA, RTFS_P_BN_BETA, d.P * 256), (int)d.P, d.B};
+    StoreEpi ep{a1, 256, c.P[RTFS_P_BN_B]};
+    CK((launch_gemm<128, 256, false>(al, c.P[RTFS_P_BN_W], ep, (int)(d.B * d.P), 256, c.st)));
+    return 0;
+}
+
+// DualPathRNN.  first: g = gLN(d1_pre) + pool is formed here and written to g_first.
+int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_first, float* g_out) {
+    const Dims& d = c.d;
+    const int base = which == 0 ? RTFS_P_RF_LNG : RTFS_P_RT_LNG;
+    const int S = which == 0 ? d.Fc : d.Tc;
+    const int n_other = which == 0 ? d.Tc : d.Fc;
+    const int nseq = d.B * n_other;
+    const int L = S - 7;
+    if (L < 1) return fail_msg("dual-path RNN needs at least 8 steps along the scanned axis");
+    const int M = nseq * S;
+    float* n = c.buf(RTFS_WS_N);
+    float* U = c.buf(RTFS_WS_U);
+    float* hA = c.buf(RTFS_WS_HA);
+    float* hB = c.buf(RTFS_WS_HB);
+    float* hpad = c.buf(RTFS_WS_HPAD);
+
+    PrepArgs pa;
+    pa.g_in = g_in;
+    pa.d1_pre = c.buf(RTFS_WS_D1_PRE);
+    pa.pool = c.buf(RTFS_WS_POOL);
+    pa.gln = c.gln(RTFS_ST_D1, RTFS_P_D1_GAMMA, RTFS_P_D1_BETA, d.Pc * 64);
+    pa.ln_gamma = c.P[base + 0];
+    pa.ln_beta = c.P[base + 1];
+    pa.g_out = g_first;
+    pa.n_out = n;
+    pa.B = d.B;
+    pa.Tc = d.Tc;
+    pa.Fc = d.Fc;
+    pa.time_path = which;
+    pa.first = first ? 1 : 0;
+    const long long npos = d.B * d.Pc;
+    dprnn_prep_kernel<<<(unsigned)((npos + 15) / 16), 256, 0, c.st>>>(pa);
+    CK(cudaGetLastError());
+    const float* resid = first ? g_first : g_in;
+
+    // layer 0: unfold(8) + Linear(512 -> 256) as a GEMM over the overlapping row view of n
+    {
+        PlainLoader al{n, 64, 512};
+        StoreEpi ep{U, 256, nullptr};
+        CK((launch_gemm<128, 512, false>(al, c.P[base + 2], ep, M, 256, c.st)));
+        ScanArgs sa{U, 256, nullptr, c.P[base + 3], c.P[base + 4], hA, nseq, S, L, 4, S, 0, 0};
+        sru_scan_kernel<<<(nseq + 3) / 4, 256, 0, c.st>>>(sa);
+        CK(cudaGetLastError());
+    }
+    float* hin = hA;
+    for (int l = 1; l <= 3; ++l) {
+        const int pw = base + 2 + 3 * l;
+        PlainLoader al{hin, 64, 64};
+        StoreEpi ep{U, 192, nullptr};
+        CK((launch_gemm<64, 64, false>(al, c.P[pw], ep, M, 192, c.st)));
+        const bool last = l == 3;
+        float* hout = last ? hpad : (hin == hA ? hB : hA);
+        ScanArgs sa{U, 192, hin, c.P[pw + 1], c.P[pw + 2], hout, nseq, S, L, 3, last ? S + 7 : S, last ? 7 : 0, last ? 1 : 0};
+        sru_scan_kernel<<<(nseq + 3) / 4, 256, 0, c.st>>>(sa);
+        CK(cudaGetLastError());
+        hin = hout;
+    }
+    // ConvTranspose1d(64,64,8) + bias + residual as a GEMM over the overlapping view of the padded h
+    {
+        PlainLoader al{hpad, 64, 512};
+        ConvTEpi ep{g_out, resid, c.P[base + 15], S, n_other, which, d.Tc, d.Fc};
+        CK((launch_gemm<64, 512, false>(al, c.P[base + 14], ep, nseq * (S + 7), 64, c.st)));
+    }
+    return 0;
+}
+
+int run_mhsa(const Ctx& c, const float* g_in, float* g_out) {
+    const Dims& d = c.d;
+    const int H = 4;
+    RowblockArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.x = g_in;
+    ra.W = c.P[RTFS_P_AT_WQKV];
+    ra.bias = c.P[RTFS_P_AT_BQKV];
+    ra.slope = c.P[RTFS_P_AT_SLOPE];
+    ra.gamma = c.P[RTFS_P_AT_GAMMA];
+    ra.beta = c.P[RTFS_P_AT_BETA];
+    ra.q = c.buf(RTFS_WS_Q);
+    ra.k = c.buf(RTFS_WS_K);
+    ra.v = c.buf(RTFS_WS_V);
+    ra.B = d.B;
+    ra.Tc = d.Tc;
+    ra.H = H;
+    {
+        static bool cfg = false;
+        const int smem = rowblock_smem_floats<96>() * 4;
+        if (!cfg) {
+            CK(cudaFuncSetAttribute(rowblock_ln_kernel<96, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            cfg = true;
+        }
+        rowblock_ln_kernel<96, 0><<<d.B * d.Tc, 128, smem, c.st>>>(ra);
+        CK(cudaGetLastError());
+    }
+    {
+        AttnArgs aa;
+        aa.q = ra.q;
+        aa.k = ra.k;
+        aa.v = ra.v;
+        aa.o = c.buf(RTFS_WS_AO);
+        aa.Tc = d.Tc;
+        aa.H = H;
+        aa.tk_pad = ((d.Tc + 63) / 64) * 64;
+        aa.scale = 1.f / sqrtf(4.f * 64.f);
+        const int smem = attn_smem_floats(aa.tk_pad) * 4;
+        if (smem > 227 * 1024) return fail_msg("attention: too many frames for the shared-memory score tile");
+        static int cfg_smem = 0;
+        if (smem > cfg_smem) {
+            CK(cudaFuncSetAttribute(attn_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            cfg_smem = smem;
+        }
+        attn_core_kernel<<<dim3((d.Tc + AT_QT - 1) / AT_QT, d.B * H), 256, smem, c.st>>>(aa);
+        CK(cudaGetLastError());
+    }
+    {
+        RowblockArgs rb;
+        memset(&rb, 0, sizeof(rb));
+        rb.x = c.buf(RTFS_WS_AO);
+        rb.resid = g_in;
+        rb.W = c.P[RTFS_P_AT_WO];
+        rb.bias = c.P[RTFS_P_AT_BO];
+        rb.slope = c.P[RTFS_P_AT_SLOPEO];
+        rb.gamma = c.P[RTFS_P_AT_GAMMAO];
+        rb.beta = c.P[RTFS_P_AT_BETAO];
+        rb.out = g_out;
+        rb.B = d.B;
+        rb.Tc = d.Tc;
+        rb.H = H;
+        static bool cfg = false;
+        const int smem = rowblock_smem_floats<64>() * 4;
+        if (!cfg) {
+            CK(cudaFuncSetAttribute(rowblock_ln_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            cfg = true;
+        }
+        rowblock_ln_kernel<64, 1><<<d.B * d.Tc, 128, smem, c.st>>>(rb);
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+int run_block(const Ctx& c, const float* x, const float* addend, float* out) {
+    const Dims& d = c.d;
+    const float* const* P = c.P;
+    const int M = (int)(d.B * d.P);
+    const long long nfull = d.P * 64, ncomp = d.Pc * 64;
+    float *p_pre = c.buf(RTFS_WS_P_PRE), *d0_pre = c.buf(RTFS_WS_D0_PRE), *d1_pre = c.buf(RTFS_WS_D1_PRE);
+    float *pool = c.buf(RTFS_WS_POOL), *g0 = c.buf(RTFS_WS_G0), *g1 = c.buf(RTFS_WS_G1), *g2 = c.buf(RTFS_WS_G2), *g3 = c.buf(RTFS_WS_G3);
+    float *le0 = c.buf(RTFS_WS_LE0_PRE), *lec = c.buf(RTFS_WS_LEC_PRE), *le1 = c.buf(RTFS_WS_LE1);
+    float *ge0 = c.buf(RTFS_WS_GE0), *gg0 = c.buf(RTFS_WS_GG0), *ge1 = c.buf(RTFS_WS_GE1), *gg1 = c.buf(RTFS_WS_GG1);
+    float *gec = c.buf(RTFS_WS_GEC), *ggc = c.buf(RTFS_WS_GGC);
+    const int tseg_full = 32, tseg_comp = 16;
+
+    CK(cudaMemsetAsync(c.stat(RTFS_ST_PJ), 0, sizeof(double) * 2 * d.B * (RTFS_ST_COUNT - RTFS_ST_PJ), c.st));
+    // S1 gateway + projection (+ gLN statistics)                         tdanet.py:34-49,107-108
+    {
+        GateLoader al{x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], 256};
+        StatsEpi ep{p_pre, 64, P[RTFS_P_PJ_B], c.stat(RTFS_ST_PJ), (int)d.P, d.B};
+        CK((launch_gemm<64, 256, false>(al, P[RTFS_P_PJ_W], ep, M, 64, c.st)));
+    }
+    // S2 PReLU(gLN(p)) -> dw4x4 s1 -> d0_pre                              tdanet.py:61-68,113
+    {
+        XfGln<2> xf{p_pre, d.T, d.F, c.gln(RTFS_ST_PJ, RTFS_P_PJ_GAMMA, RTFS_P_PJ_BETA, nfull), P[RTFS_P_PJ_A]};
+        DwArgs<1> a{d.T, d.F, d.T, d.F, tseg_full, {P[RTFS_P_D0_W]}, {P[RTFS_P_D0_B]}, {d0_pre}, {c.stat(RTFS_ST_D0)}, nullptr};
+        CK((launch_dw<1, 4, 1, false>(xf, a, d.B, c.st)));
+    }
+    // S3 gLN(d0_pre) -> dw4x4 s2 -> d1_pre ; adaptive_avg_pool2d(d0) -> pool    tdanet.py:69-76,114-118
+    {
+        XfGln<0> xf{d0_pre, d.T, d.F, c.gln(RTFS_ST_D0, RTFS_P_D0_GAMMA, RTFS_P_D0_BETA, nfull), nullptr};
+        DwArgs<1> a{d.T, d.F, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_D1_W]}, {P[RTFS_P_D1_B]}, {d1_pre}, {c.stat(RTFS_ST_D1)}, pool};
+        CK((launch_dw<2, 2, 1, true>(xf, a, d.B, c.st)));
+    }
+    // S4-S9 global attention stack                                         tdanet.py:121
+    RUN(run_dprnn(c, 0, true, nullptr, g0, g1));
+    RUN(run_dprnn(c, 1, false, g1, nullptr, g2));
+    RUN(run_mhsa(c, g2, g3));
+    // S10-S12 TF-AR units                                                  tdanet.py:124-129, layers/fusion.py:54-69
+    {
+        XfPlain xf{g3, d.Tc, d.Fc};
+        DwArgs<2> a0{d.Tc, d.Fc, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_F0_EW], P[RTFS_P_F0_GW]}, {nullptr, nullptr}, {ge0, gg0}, {c.stat(RTFS_ST_F0E), c.stat(RTFS_ST_F0G)}, nullptr};
+        CK((launch_dw<1, 2, 2, false>(xf, a0, d.B, c.st)));
+        DwArgs<2> a1{d.Tc, d.Fc, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_F1_EW], P[RTFS_P_F1_GW]}, {nullptr, nullptr}, {ge1, gg1}, {c.stat(RTFS_ST_F1E), c.stat(RTFS_ST_F1G)}, nullptr};
+        CK((launch_dw<1, 2, 2, false>(xf, a1, d.B, c.st)));
+    }
+    {
+        XfGln<0> xf{d1_pre, d.Tc, d.Fc, c.gln(RTFS_ST_D1, RTFS_P_D1_GAMMA, RTFS_P_D1_BETA, ncomp), nullptr};
+        DwArgs<1> a{d.Tc, d.Fc, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_F1_LW]}, {nullptr}, {le1}, {c.stat(RTFS_ST_F1L)}, nullptr};
+        CK((launch_dw<1, 4, 1, false>(xf, a, d.B, c.st)));
+    }
+    {
+        XfGln<0> xf{d0_pre, d.T, d.F, c.gln(RTFS_ST_D0, RTFS_P_D0_GAMMA, RTFS_P_D0_BETA, nfull), nullptr};
+        DwArgs<1> a{d.T, d.F, d.T, d.F, tseg_full, {P[RTFS_P_F0_LW]}, {nullptr}, {le0}, {c.stat(RTFS_ST_F0L)}, nullptr};
+        CK((launch_dw<1, 4, 1, false>(xf, a, d.B, c.st)));
+    }
+    {
+        // f1 = TFAR_fus1(d1, g) formed on the fly -> the two global convs of concat_layers.0
+        XfTfar xf{le1, gg1, ge1, d.Tc, d.Fc, d.Tc, d.Fc,
+                  c.gln(RTFS_ST_F1L, RTFS_P_F1_LG, RTFS_P_F1_LB, ncomp), c.gln(RTFS_ST_F1G, RTFS_P_F1_GG, RTFS_P_F1_GB, ncomp),
+                  c.gln(RTFS_ST_F1E, RTFS_P_F1_EG, RTFS_P_F1_EB, ncomp)};
+        DwArgs<2> a{d.Tc, d.Fc, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_C0_EW], P[RTFS_P_C0_GW]}, {nullptr, nullptr}, {gec, ggc}, {c.stat(RTFS_ST_C0E), c.stat(RTFS_ST_C0G)}, nullptr};
+        CK((launch_dw<1, 2, 2, false>(xf, a, d.B, c.st)));
+    }
+    {
+        // f0 = TFAR_fus0(d0, g) formed on the fly -> local conv of concat_layers.0
+        XfTfar xf{le0, gg0, ge0, d.T, d.F, d.Tc, d.Fc,
+                  c.gln(RTFS_ST_F0L, RTFS_P_F0_LG, RTFS_P_F0_LB, nfull), c.gln(RTFS_ST_F0G, RTFS_P_F0_GG, RTFS_P_F0_GB, ncomp),
+                  c.gln(RTFS_ST_F0E, RTFS_P_F0_EG, RTFS_P_F0_EB, ncomp)};
+        DwArgs<1> a{d.T, d.F, d.T, d.F, tseg_full, {P[RTFS_P_C0_LW]}, {nullptr}, {lec}, {c.stat(RTFS_ST_C0L)}, nullptr};
+        CK((launch_dw<1, 4, 1, false>(xf, a, d.B, c.st)));
+    }
+    // S13 e = TFAR_cat0(f0,f1) + d0 on the fly -> residual_conv + gateway(x) [+ addend]     tdanet.py:127-131
+    {
+        TfarLoader al;
+        al.lec = lec;
+        al.d0 = d0_pre;
+        al.ggc = ggc;
+        al.gec = gec;
+        al.n_l = c.gln(RTFS_ST_C0L, RTFS_P_C0_LG, RTFS_P_C0_LB, nfull);
+        al.n_d = c.gln(RTFS_ST_D0, RTFS_P_D0_GAMMA, RTFS_P_D0_BETA, nfull);
+        al.n_g = c.gln(RTFS_ST_C0G, RTFS_P_C0_GG, RTFS_P_C0_GB, ncomp);
+        al.n_e = c.gln(RTFS_ST_C0E, RTFS_P_C0_EG, RTFS_P_C0_EB, ncomp);
+        al.T = d.T;
+        al.F = d.F;
+        al.Tc = d.Tc;
+        al.Fc = d.Fc;
+        al.B = d.B;
+        ResidOutEpi ep{out, P[RTFS_P_RC_B], x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], addend, 0.f};
+        CK((launch_gemm<128, 64, false>(al, P[RTFS_P_RC_W], ep, M, 256, c.st)));
+    }
+    return 0;
+}
+
+int run_caf(const Ctx& c, const float* audio, const float* video, const float* addend, float* out) {
+    const Dims& d = c.d;
+    const float* const* P = c.P;
+    CafVideoArgs va{video, P[RTFS_P_CAF_WR], P[RTFS_P_CAF_BR], P[RTFS_P_CAF_GR], P[RTFS_P_CAF_BER],
+                    P[RTFS_P_CAF_WA], P[RTFS_P_CAF_BA], P[RTFS_P_CAF_GA], P[RTFS_P_CAF_BEA],
+                    c.buf(RTFS_WS_VK), c.buf(RTFS_WS_ATT), 256, d.Tv};
+    const int smem = d.Tv * 256 * 4;
+    if (smem > 200 * 1024) return fail_msg("CAF: too many video frames for the shared-memory softmax");
+    static int cfg_smem = 48 * 1024;
+    if (smem > cfg_smem) {
+        CK(cudaFuncSetAttribute(caf_video_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        cfg_smem = smem;
+    }
+    caf_video_kernel<<<d.B, 256, smem, c.st>>>(va);
+    CK(cudaGetLastError());
+    CafApplyArgs aa{audio, addend, c.buf(RTFS_WS_VK), c.buf(RTFS_WS_ATT), P[RTFS_P_CAF_SK], P[RTFS_P_CAF_TK],
+                    P[RTFS_P_CAF_SV], P[RTFS_P_CAF_TV], out, d.T, d.F, 256, d.Tv, d.B * d.P * 64};
+    long long blocks = (aa.total4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    caf_apply_kernel<<<(unsigned)blocks, 256, 0, c.st>>>(aa);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int run_mask(const Ctx& c, const float* refined, const float* a0, float* z) {
+    const Dims& d = c.d;
+    PreluLoader al{refined, c.P[RTFS_P_MK_A], 256};
+    MaskEpi ep{z, c.P[RTFS_P_MK_B], a0};
+    CK((launch_gemm<128, 256, false>(al, c.P[RTFS_P_MK_W], ep, (int)(d.B * d.P), 256, c.st)));
+    return 0;
+}
+
+int run_decoder(const Ctx& c, const float* z, float* wav_out, int L) {
+    const Dims& d = c.d;
+    PlainLoader al{z, 256, 256};
+    StoreEpi ep{c.buf(RTFS_WS_Q18), 18, nullptr};
+    CK((launch_gemm<32, 256, true>(al, c.P[RTFS_P_DEC_W], ep, (int)(d.B * d.P), 18, c.st)));
+    IstftArgs ia{c.buf(RTFS_WS_Q18), c.P[RTFS_P_WINDOW], c.P[RTFS_P_COSTAB], c.P[RTFS_P_SINTAB], wav_out, L, d.T};
+    dec_istft_kernel<<<dim3((L + 127) / 128, d.B), 256, 0, c.st>>>(ia);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+bool make_ctx(Ctx& c, const float* const* params, void* ws, int B, int T, int Tv, void* stream) {
+    if (params == nullptr || B < 1 || T < 16) {
+        g_err = "bad arguments (params null, B < 1 or fewer than 16 frames)";
+        return false;
+    }
+    c.P = params;
+    c.d = make_dims(B, T, Tv);
+    if ((long long)B * c.d.P * 256 >= (1ll << 31)) {
+        g_err = "batch too large for 32-bit row indexing (B*T*F*256 must be < 2^31 elements per call)";
+        return false;
+    }
+    c.pl = make_plan(c.d);
+    c.ws = reinterpret_cast<char*>(ws);
+    c.st = reinterpret_cast<cudaStream_t>(stream);
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rtfs_abi_version(void) { return RTFS_ABI_VERSION; }
+const char* rtfs_last_error(void) { return g_err.c_str(); }
+long long rtfs_last_launch_count(void) { return g_launches; }
+
+long long rtfs_ws_plan(int B, int L, int Tv, long long* offsets) {
+    const Dims d = make_dims(B, L / 128 + 1, Tv);
+    const Plan p = make_plan(d);
+    if (offsets)
+        for (int i = 0; i < RTFS_WS_COUNT; ++i) offsets[i] = p.off[i];
+    return p.total;
+}
+
+int rtfs_encoder_forward(const float* const* params, const float* wav, float* a0, void* ws, int B, int L, void* stream) {
+    Ctx c;
+    if (!make_ctx(c, params, ws, B, L / 128 + 1, 0, stream)) return -2;
+    return run_encoder(c, wav, a0, L);
+}
+
+int rtfs_bottleneck_forward(const float* const* params, const float* a0, float* a1, void* ws, int B, int T, void* stream) {
+    Ctx c;
+    if (!make_ctx(c, params, ws, B, T, 0, stream)) return -2;
+    return run_bottleneck(c, a0, a1, true);
+}
+
+int rtfs_block_forward(const float* const* params, const float* x, const float* addend, float* out, void* ws, int B, int T, void* stream) {
+    Ctx c;
+    if (!make_ctx(c, params, ws, B, T, 0, stream)) return -2;
+    if (x == out) return fail_msg("rtfs_block_forward: out must not alias x");
+    return run_block(c, x, addend, out);
+}
+
+int rtfs_dprnn_forward(const float* const* params, int which, const float* g_in, float* g_out, void* ws, int B, int T, void* stream) {
+    Ctx c;
+    if (!make_ctx(c, params, ws, B, T, 0, stream)) return -2;
+    return run_dprnn(c, which, false, g_in, nullptr, g_out);
+}
+
+int rtfs_mhsa_forward(const float* const* params, const float* g_in, float* g_out, void* ws, int B, int T, void* stream) {
+    Ctx c;
+    if (!make_ctx(c, params, ws, B, T, 0, stream)) return -2;
+    return run_mhsa(c, g_in, g_out);
+}
+
+int rtfs_caf_forward(const float* const* params, const float* audio, const float* video, const float* addend, float* out, void* ws, int B, int T, int Tv, void* stream) {
+    Ctx c;
+    if (!make_ctx(c, params, ws, B, T, Tv, stream)) return -2;
+    if (Tv < 1) return fail_msg("rtfs_caf_forward: Tv < 1");
+    return run_caf(c, audio, video, addend, out);
+}
+
+int rtfs_mask_forward(const float* const* params, const float* refined, const float* a0, float* z, int B, int T, void* stream) {
+    Ctx c;
+    if (!make_ctx(c, params, nullptr, B, T, 0, stream)) return -2;
+    return run_mask(c, refined, a0, z);
+}
+
+int rtfs_decoder_forward(const float* const* params, const float* z, float* wav_out, void* ws, int B, int L, void* stream) {
+    Ctx c;
+    if (!make_ctx(c, params, ws, B, L / 128 + 1, 0, stream)) return -2;
+    return run_decoder(c, z, wav_out, L);
+}
+
+int rtfs_avnet_forward(const float* const* params, const float* wav, const float* video, float* out, void* ws, int B, int L, int Tv, int repeats, void* stream) {
+    Ctx c;
+    if (!make_ctx(c, params, ws, B, L / 128 + 1, Tv, stream)) return -2;
+    if (repeats < 1 || Tv < 1) return fail_msg("rtfs_avnet_forward: repeats < 1 or Tv < 1");
+    g_launches = 0;
+    float *a0 = c.buf(RTFS_WS_A0), *a1 = c.buf(RTFS_WS_A1), *xa = c.buf(RTFS_WS_XA), *xb = c.buf(RTFS_WS_XB);
+    RUN(run_encoder(c, wav, a0, L));
+    RUN(run_bottleneck(c, a0, a1, false));
+    // refinement_module.py:45-62 with fusion_repeats = 1
+    RUN(run_block(c, a1, nullptr, xa));
+    RUN(run_caf(c, xa, video, repeats > 1 ? a1 : nullptr, xb));
+    float *cur = xb, *other = xa;
+    for (int i = 1; i < repeats; ++i) {
+        RUN(run_block(c, cur, (i + 1 < repeats) ? a1 : nullptr, other));
+        float* t = cur;
+        cur = other;
+        other = t;
+    }
+    RUN(run_mask(c, cur, a0, a1));  // a1 is dead by now: reuse it for z
+    RUN(run_decoder(c, a1, out, L));
+    return 0;
+}
+
+}  // extern "C"

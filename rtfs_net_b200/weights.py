@@ -1,0 +1,160 @@
+"""Host-side preparation of the reference's parameters into the kernel layouts of
+include/rtfs_b200.h (enum rtfs_param).  Input: a state_dict with the reference's key names
+(SURVEY.md App. B); output: one contiguous fp32 tensor per slot on the target device.
+
+Done once per parameter version (not on the hot path): TF32 rounding of GEMM weights (cvt.rna),
+K/N permutations that turn nn.Unfold / ConvTranspose1d / channel concatenation into plain
+row-major GEMMs, tap-major depthwise filters, folded eval-mode BatchNorm.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+
+BLK = "refinement_module.audio_net.blocks."
+CAF = "refinement_module.crossmodal_fusion.fusion_module.audio_lstm."
+
+
+def tf32_round(x: torch.Tensor) -> torch.Tensor:
+    """cvt.rna.tf32.f32: round to nearest (ties away from zero) to a 10-bit mantissa."""
+    i = x.detach().to(torch.float32).contiguous().view(torch.int32)
+    i = (i + 0x1000) & -8192
+    return i.view(torch.float32)
+
+
+def _tapmajor(w):
+    """depthwise (C,1,4,4) -> [16][C]"""
+    C = w.shape[0]
+    return w.reshape(C, -1).t().contiguous()
+
+
+def prepare(sd, device):
+    """state_dict -> {slot name: tensor}"""
+    g = lambda k: sd[k].detach().to(device=device, dtype=torch.float32)
+    out = {}
+    out["RTFS_P_WINDOW"] = torch.hann_window(256, periodic=True, dtype=torch.float32, device=device)
+    k = torch.arange(256, dtype=torch.float64)
+    out["RTFS_P_COSTAB"] = torch.cos(2.0 * math.pi * k / 256).to(torch.float32).to(device)
+    out["RTFS_P_SINTAB"] = torch.sin(2.0 * math.pi * k / 256).to(torch.float32).to(device)
+
+    w = g("encoder.conv.full_layer.2.weight")  # (256,2,3,3) [co,ci,i,j] -> k = (i*3+j)*2+ci
+    enc = torch.zeros(256, 32, device=device)
+    enc[:, :18] = w.permute(0, 2, 3, 1).reshape(256, 18)
+    out["RTFS_P_ENC_W"] = enc
+
+    out["RTFS_P_BN_GAMMA"] = g("audio_bottleneck.full_layer.0.norm.weight")
+    out["RTFS_P_BN_BETA"] = g("audio_bottleneck.full_layer.0.norm.bias")
+    out["RTFS_P_BN_W"] = tf32_round(g("audio_bottleneck.full_layer.2.weight").reshape(256, 256))
+    out["RTFS_P_BN_B"] = g("audio_bottleneck.full_layer.2.bias")
+
+    out["RTFS_P_GW_W"] = g(BLK + "gateway.full_layer.2.weight").reshape(-1)
+    out["RTFS_P_GW_B"] = g(BLK + "gateway.full_layer.2.bias")
+    out["RTFS_P_GW_A"] = g(BLK + "gateway.full_layer.4.weight").reshape(1)
+    out["RTFS_P_PJ_W"] = tf32_round(g(BLK + "projection.full_layer.2.weight").reshape(64, 256))
+    out["RTFS_P_PJ_B"] = g(BLK + "projection.full_layer.2.bias")
+    out["RTFS_P_PJ_GAMMA"] = g(BLK + "projection.full_layer.3.norm.weight")
+    out["RTFS_P_PJ_BETA"] = g(BLK + "projection.full_layer.3.norm.bias")
+    out["RTFS_P_PJ_A"] = g(BLK + "projection.full_layer.4.weight").reshape(1)
+    for i in (0, 1):
+        q = BLK + f"downsample_layers.{i}.full_layer."
+        out[f"RTFS_P_D{i}_W"] = _tapmajor(g(q + "2.weight"))
+        out[f"RTFS_P_D{i}_B"] = g(q + "2.bias")
+        out[f"RTFS_P_D{i}_GAMMA"] = g(q + "3.norm.weight")
+        out[f"RTFS_P_D{i}_BETA"] = g(q + "3.norm.bias")
+
+    for r, tag in ((0, "RF"), (1, "RT")):
+        q = BLK + f"globalatt.{r}."
+        out[f"RTFS_P_{tag}_LNG"] = g(q + "norm.gamma").reshape(64)
+        out[f"RTFS_P_{tag}_LNB"] = g(q + "norm.beta").reshape(64)
+        w0 = g(q + "rnn.rnn_lst.0.weight")  # (512,256): rows c*8+tap, cols col*4+m
+        # -> [m*64+col][tap*64+c]
+        out[f"RTFS_P_{tag}_W0"] = tf32_round(w0.view(64, 8, 64, 4).permute(3, 2, 1, 0).reshape(256, 512))
+        out[f"RTFS_P_{tag}_WC0"] = g(q + "rnn.rnn_lst.0.weight_c")
+        out[f"RTFS_P_{tag}_B0"] = g(q + "rnn.rnn_lst.0.bias")
+        for l in (1, 2, 3):
+            wl = g(q + f"rnn.rnn_lst.{l}.weight")  # (64,192): rows ci, cols col*3+m -> [m*64+col][ci]
+            out[f"RTFS_P_{tag}_W{l}"] = tf32_round(wl.view(64, 64, 3).permute(2, 1, 0).reshape(192, 64))
+            out[f"RTFS_P_{tag}_WC{l}"] = g(q + f"rnn.rnn_lst.{l}.weight_c")
+            out[f"RTFS_P_{tag}_B{l}"] = g(q + f"rnn.rnn_lst.{l}.bias")
+        wct = g(q + "linear.weight")  # ConvTranspose1d (ci, co, tap) -> [co][(7-tap)*64+ci]
+        out[f"RTFS_P_{tag}_CTW"] = tf32_round(wct.flip(2).permute(1, 2, 0).reshape(64, 512))
+        out[f"RTFS_P_{tag}_CTB"] = g(q + "linear.bias")
+
+    a = BLK + "globalatt.2."
+    n_head = 0
+    while (a + f"Queries.{n_head}.conv.weight") in sd:
+        n_head += 1
+    if n_head != 4:
+        raise NotImplementedError("the attention kernels are built for n_head = 4 (RTFS-Net configs)")
+    ws, bs, sl, gm, bt = [], [], [], [], []
+    for kind in ("Queries", "Keys", "Values"):
+        for h in range(n_head):
+            p = a + f"{kind}.{h}."
+            wk = g(p + "conv.weight")
+            E = wk.shape[0]
+            ws.append(wk.reshape(E, 64))
+            bs.append(g(p + "conv.bias"))
+            sl.append(g(p + "act.weight").reshape(1))
+            gm.append(g(p + "norm.gamma").reshape(E, 64).t().reshape(-1))  # [f*E+e]
+            bt.append(g(p + "norm.beta").reshape(E, 64).t().reshape(-1))
+    out["RTFS_P_AT_WQKV"] = tf32_round(torch.cat(ws, 0))
+    out["RTFS_P_AT_BQKV"] = torch.cat(bs)
+    out["RTFS_P_AT_SLOPE"] = torch.cat(sl)
+    out["RTFS_P_AT_GAMMA"] = torch.cat(gm)
+    out["RTFS_P_AT_BETA"] = torch.cat(bt)
+    p = a + "attn_concat_proj."
+    out["RTFS_P_AT_WO"] = tf32_round(g(p + "conv.weight").reshape(64, 64))
+    out["RTFS_P_AT_BO"] = g(p + "conv.bias")
+    out["RTFS_P_AT_SLOPEO"] = g(p + "act.weight").reshape(1)
+    out["RTFS_P_AT_GAMMAO"] = g(p + "norm.gamma").reshape(64, 64).t().reshape(-1)  # [f*64+c]
+    out["RTFS_P_AT_BETAO"] = g(p + "norm.beta").reshape(64, 64).t().reshape(-1)
+
+    for tag, key in (("F0", "fusion_layers.0."), ("F1", "fusion_layers.1."), ("C0", "concat_layers.0.")):
+        for x, sub in (("L", "local_embedding."), ("E", "global_embedding."), ("G", "global_gate.")):
+            q = BLK + key + sub + "full_layer."
+            out[f"RTFS_P_{tag}_{x}W"] = _tapmajor(g(q + "2.weight"))
+            out[f"RTFS_P_{tag}_{x}G"] = g(q + "3.norm.weight")
+            out[f"RTFS_P_{tag}_{x}B"] = g(q + "3.norm.bias")
+    out["RTFS_P_RC_W"] = tf32_round(g(BLK + "residual_conv.full_layer.2.weight").reshape(256, 64))
+    out["RTFS_P_RC_B"] = g(BLK + "residual_conv.full_layer.2.bias")
+
+    out["RTFS_P_CAF_WR"] = g(CAF + "resize.full_layer.2.weight").reshape(-1)
+    out["RTFS_P_CAF_BR"] = g(CAF + "resize.full_layer.2.bias")
+    out["RTFS_P_CAF_GR"] = g(CAF + "resize.full_layer.3.norm.weight")
+    out["RTFS_P_CAF_BER"] = g(CAF + "resize.full_layer.3.norm.bias")
+    out["RTFS_P_CAF_WA"] = g(CAF + "attention_embed.full_layer.2.weight").reshape(-1)
+    out["RTFS_P_CAF_BA"] = g(CAF + "attention_embed.full_layer.2.bias")
+    out["RTFS_P_CAF_GA"] = g(CAF + "attention_embed.full_layer.3.norm.weight")
+    out["RTFS_P_CAF_BEA"] = g(CAF + "attention_embed.full_layer.3.norm.bias")
+    for name, s_slot, t_slot in (("key_embed", "SK", "TK"), ("value_embed", "SV", "TV")):
+        q = CAF + name + ".full_layer."
+        wdw = g(q + "2.weight").reshape(-1)
+        inv = g(q + "3.weight") / torch.sqrt(g(q + "3.running_var") + 1e-5)
+        out[f"RTFS_P_CAF_{s_slot}"] = wdw * inv
+        out[f"RTFS_P_CAF_{t_slot}"] = g(q + "3.bias") - g(q + "3.running_mean") * inv
+
+    out["RTFS_P_MK_A"] = g("mask_generator.mask_generator.0.weight").reshape(1)
+    perm = torch.stack([torch.arange(128), torch.arange(128) + 128], 1).reshape(-1).to(device)
+    out["RTFS_P_MK_W"] = tf32_round(g("mask_generator.mask_generator.1.full_layer.2.weight").reshape(256, 256)[perm])
+    out["RTFS_P_MK_B"] = g("mask_generator.mask_generator.1.full_layer.2.bias")[perm].contiguous()
+    out["RTFS_P_DEC_W"] = g("decoder.decoder.weight").permute(1, 2, 3, 0).reshape(18, 256).contiguous()
+
+    missing = [n for n in _lib.PARAM_NAMES if n not in out]
+    if missing:
+        raise RuntimeError(f"unprepared parameter slots: {missing}")
+    return {n: out[n].contiguous() for n in _lib.PARAM_NAMES}
+
+
+class PackedParams:
+    """The pointer table passed as `params` to every C-ABI call (keeps the tensors alive)."""
+
+    def __init__(self, sd, device):
+        self.device = torch.device(device)
+        self.tensors = prepare(sd, self.device)
+        self.table = (ctypes.c_void_p * len(_lib.PARAM_NAMES))(*[self.tensors[n].data_ptr() for n in _lib.PARAM_NAMES])
+
+    @property
+    def ptr(self):
+        return ctypes.cast(self.table, ctypes.c_void_p)
