@@ -220,8 +220,9 @@ def mhsa2d(sd, p, x):
     return conv_act_norm(sd, p + "attn_concat_proj.", y) + x
 
 
-def tfar(sd, p, local, glob):
-    """InjectionMultiSum.forward (TF-AR unit), layers/fusion.py:54-69.  1-D or 2-D by rank."""
+def tfar(sd, p, local, glob, taps=None, tag=""):
+    """InjectionMultiSum.forward (TF-AR unit), layers/fusion.py:54-69.  1-D or 2-D by rank.
+    `taps` (test instrumentation only) receives the pre-norm conv outputs."""
     two_d = local.ndim == 4
     dw = dwconv2d if two_d else dwconv1d
     up = nearest2d if two_d else nearest1d
@@ -230,14 +231,19 @@ def tfar(sd, p, local, glob):
     n_loc = math.prod(local.shape[2:])
     n_glob = math.prod(glob.shape[2:])
     lw = sd[p + "local_embedding.full_layer.2.weight"]
-    local_emb = norm_p(p + "local_embedding.", dw(local, lw, None, 1))
+    l_pre = dw(local, lw, None, 1)
+    local_emb = norm_p(p + "local_embedding.", l_pre)
+    gi = glob if n_loc > n_glob else up(glob, loc_shape)
+    e_pre = dw(gi, sd[p + "global_embedding.full_layer.2.weight"], None, 1)
+    g_pre = dw(gi, sd[p + "global_gate.full_layer.2.weight"], None, 1)
     if n_loc > n_glob:
-        ge = up(norm_p(p + "global_embedding.", dw(glob, sd[p + "global_embedding.full_layer.2.weight"], None, 1)), loc_shape)
-        gate = up(torch.sigmoid(norm_p(p + "global_gate.", dw(glob, sd[p + "global_gate.full_layer.2.weight"], None, 1))), loc_shape)
+        ge = up(norm_p(p + "global_embedding.", e_pre), loc_shape)
+        gate = up(torch.sigmoid(norm_p(p + "global_gate.", g_pre)), loc_shape)
     else:
-        gi = up(glob, loc_shape)
-        ge = norm_p(p + "global_embedding.", dw(gi, sd[p + "global_embedding.full_layer.2.weight"], None, 1))
-        gate = torch.sigmoid(norm_p(p + "global_gate.", dw(gi, sd[p + "global_gate.full_layer.2.weight"], None, 1)))
+        ge = norm_p(p + "global_embedding.", e_pre)
+        gate = torch.sigmoid(norm_p(p + "global_gate.", g_pre))
+    if taps is not None:
+        taps.update({tag + "_l_pre": l_pre, tag + "_e_pre": e_pre, tag + "_g_pre": g_pre})
     return local_emb * gate + ge
 
 
@@ -256,26 +262,30 @@ def rtfs_block(sd, p, x, taps=None):
     separators/tdanet.py:106-133."""
     r = prelu(x * sd[p + "gateway.full_layer.2.weight"].view(1, -1, 1, 1) + sd[p + "gateway.full_layer.2.bias"].view(1, -1, 1, 1),
               sd[p + "gateway.full_layer.4.weight"])
-    pp = F.conv2d(r, sd[p + "projection.full_layer.2.weight"], sd[p + "projection.full_layer.2.bias"])
-    pp = prelu(gln(pp, sd[p + "projection.full_layer.3.norm.weight"], sd[p + "projection.full_layer.3.norm.bias"]),
+    p_pre = F.conv2d(r, sd[p + "projection.full_layer.2.weight"], sd[p + "projection.full_layer.2.bias"])
+    pp = prelu(gln(p_pre, sd[p + "projection.full_layer.3.norm.weight"], sd[p + "projection.full_layer.3.norm.bias"]),
                sd[p + "projection.full_layer.4.weight"])
     q = p + "downsample_layers.0.full_layer."
-    d0 = gln(dwconv2d(pp, sd[q + "2.weight"], sd[q + "2.bias"], 1), sd[q + "3.norm.weight"], sd[q + "3.norm.bias"])
+    d0_pre = dwconv2d(pp, sd[q + "2.weight"], sd[q + "2.bias"], 1)
+    d0 = gln(d0_pre, sd[q + "3.norm.weight"], sd[q + "3.norm.bias"])
     q = p + "downsample_layers.1.full_layer."
-    d1 = gln(dwconv2d(d0, sd[q + "2.weight"], sd[q + "2.bias"], 2), sd[q + "3.norm.weight"], sd[q + "3.norm.bias"])
-    g = F.adaptive_avg_pool2d(d0, d1.shape[-2:]) + d1  # tdanet.py:117-118 (pool of d1 to its own size = id)
+    d1_pre = dwconv2d(d0, sd[q + "2.weight"], sd[q + "2.bias"], 2)
+    d1 = gln(d1_pre, sd[q + "3.norm.weight"], sd[q + "3.norm.bias"])
+    pool = F.adaptive_avg_pool2d(d0, d1.shape[-2:])
+    g = pool + d1  # tdanet.py:117-118 (pool of d1 to its own size = id)
     g0 = g
     g = dual_path_rnn(sd, p + "globalatt.0.", g, 4)
     g1 = g
     g = dual_path_rnn(sd, p + "globalatt.1.", g, 3)
     g2 = g
     g = mhsa2d(sd, p + "globalatt.2.", g)
-    f0 = tfar(sd, p + "fusion_layers.0.", d0, g)
-    f1 = tfar(sd, p + "fusion_layers.1.", d1, g)
-    e = tfar(sd, p + "concat_layers.0.", f0, f1) + d0
+    f0 = tfar(sd, p + "fusion_layers.0.", d0, g, taps, "f0")
+    f1 = tfar(sd, p + "fusion_layers.1.", d1, g, taps, "f1")
+    e = tfar(sd, p + "concat_layers.0.", f0, f1, taps, "c0") + d0
     out = F.conv2d(e, sd[p + "residual_conv.full_layer.2.weight"], sd[p + "residual_conv.full_layer.2.bias"]) + r
     if taps is not None:
-        taps.update(dict(d0=d0, d1=d1, g0=g0, g1=g1, g2=g2, g3=g, f0=f0, f1=f1, e=e))
+        taps.update(dict(d0=d0, d1=d1, g0=g0, g1=g1, g2=g2, g3=g, f0=f0, f1=f1, e=e,
+                         p_pre=p_pre, d0_pre=d0_pre, d1_pre=d1_pre, pool=pool))
     return out
 
 
