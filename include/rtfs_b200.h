@@ -91,6 +91,17 @@ enum rtfs_stat {
     RTFS_ST_COUNT
 };
 
+/* Stages of the forward, for the optional per-stage device timing (rtfs_profile_*). */
+enum rtfs_stage {
+    RTFS_SG_STFT = 0, RTFS_SG_ENC_CONV, RTFS_SG_BOTTLENECK,
+    RTFS_SG_GATE_PROJ, RTFS_SG_DW_S1, RTFS_SG_DW_S2_POOL,
+    RTFS_SG_DPRNN_PREP, RTFS_SG_DPRNN_GEMM0, RTFS_SG_DPRNN_SCAN, RTFS_SG_DPRNN_GEMML, RTFS_SG_DPRNN_CONVT,
+    RTFS_SG_ATT_QKV, RTFS_SG_ATT_CORE, RTFS_SG_ATT_PROJ,
+    RTFS_SG_TFAR_GLOBAL, RTFS_SG_TFAR_LE0, RTFS_SG_TFAR_CAT_GLOBAL, RTFS_SG_TFAR_CAT_LOCAL, RTFS_SG_RESID_OUT,
+    RTFS_SG_CAF_VIDEO, RTFS_SG_CAF_APPLY, RTFS_SG_MASK, RTFS_SG_DEC_GEMM, RTFS_SG_DEC_ISTFT,
+    RTFS_SG_COUNT
+};
+
 int rtfs_abi_version(void);
 const char* rtfs_last_error(void);
 
@@ -135,6 +146,12 @@ int rtfs_avnet_forward(const float* const* params, const float* wav, const float
 
 /* Number of kernels the last rtfs_avnet_forward on this thread launched (bench gpu_launches). */
 long long rtfs_last_launch_count(void);
+
+/* Per-stage device timing: when enabled, every stage is bracketed by cudaEvents on the launch
+ * stream.  rtfs_profile_collect synchronises the device, adds the elapsed milliseconds and launch
+ * counts per stage into ms[RTFS_SG_COUNT] / count[RTFS_SG_COUNT], and resets the recorder. */
+void rtfs_profile_enable(int on);
+int rtfs_profile_collect(float* ms, int* count);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,8 @@ PROTOTYPES = {
     "rtfs_abi_version": (_c_i, []),
     "rtfs_last_error": (ctypes.c_char_p, []),
     "rtfs_last_launch_count": (_c_ll, []),
+    "rtfs_profile_enable": (None, [_c_i]),
+    "rtfs_profile_collect": (_c_i, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_c_i)]),
     "rtfs_ws_plan": (_c_ll, [_c_i, _c_i, _c_i, ctypes.POINTER(_c_ll)]),
     "rtfs_encoder_forward": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_p]),
     "rtfs_bottleneck_forward": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_p]),
@@ -64,6 +66,7 @@ def declared_functions(header_text=None):
 PARAM_NAMES = parse_enum("rtfs_param")[:-1]  # drop RTFS_P_COUNT
 WS_NAMES = parse_enum("rtfs_ws")[:-1]
 STAT_NAMES = parse_enum("rtfs_stat")[:-1]
+STAGE_NAMES = parse_enum("rtfs_stage")[:-1]
 P = {n: i for i, n in enumerate(PARAM_NAMES)}
 WS = {n: i for i, n in enumerate(WS_NAMES)}
 ST = {n: i for i, n in enumerate(STAT_NAMES)}
@@ -102,3 +105,16 @@ def ws_plan(B, L, Tv):
     offs = (_c_ll * len(WS_NAMES))()
     total = lib().rtfs_ws_plan(int(B), int(L), int(Tv), offs)
     return int(total), {n: int(offs[i]) for i, n in enumerate(WS_NAMES)}
+
+
+def profile_enable(on=True):
+    lib().rtfs_profile_enable(1 if on else 0)
+
+
+def profile_collect():
+    """{stage name: (total ms, launches)} since the last collect; synchronises the device."""
+    n = len(STAGE_NAMES)
+    ms = (ctypes.c_float * n)()
+    cnt = (_c_i * n)()
+    check(lib().rtfs_profile_collect(ms, cnt), "rtfs_profile_collect")
+    return {STAGE_NAMES[i]: (float(ms[i]), int(cnt[i])) for i in range(n)}

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/rtfs_b200.h"
 #include "attention.cuh"
@@ -18,6 +19,40 @@ namespace {
 
 thread_local std::string g_err;
 thread_local long long g_launches = 0;
+
+// Optional per-stage device timing (bench.py roofline leg): cudaEvent pairs recorded on the launch
+// stream around every stage; collected (and reset) by rtfs_profile_collect.
+struct Profiler {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    std::vector<int> stage;  // stage id of pair i -> events pool[2i], pool[2i+1]
+    size_t used = 0;
+    cudaEvent_t get() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+};
+thread_local Profiler g_prof;
+
+struct StageTimer {
+    cudaStream_t st;
+    cudaEvent_t stop = nullptr;
+    StageTimer(int id, cudaStream_t s) : st(s) {
+        if (!g_prof.on) return;
+        cudaEvent_t start = g_prof.get();
+        stop = g_prof.get();
+        g_prof.stage.push_back(id);
+        cudaEventRecord(start, st);
+    }
+    ~StageTimer() {
+        if (stop) cudaEventRecord(stop, st);
+    }
+};
+#define STAGE(id) StageTimer stage_timer__(id, c.st)
 
 struct Dims {
     int B, T, F, Tc, Fc, Tv;
@@ -95,10 +130,16 @@ int fail_msg(const std::string& m) {
     return -2;
 }
 
+// CK: a kernel launch (counted) ; CKN: any other runtime call
 #define CK(call)                                   \
     do {                                           \
         cudaError_t e__ = (call);                  \
         ++g_launches;                              \
+        if (e__ != cudaSuccess) return fail(#call, e__); \
+    } while (0)
+#define CKN(call)                                  \
+    do {                                           \
+        cudaError_t e__ = (call);                  \
         if (e__ != cudaSuccess) return fail(#call, e__); \
     } while (0)
 #define RUN(call)                 \
@@ -126,11 +167,15 @@ __global__ void __launch_bounds__(256) gln_stats_kernel(const float* __restrict_
 int run_encoder(const Ctx& c, const float* wav, float* a0, int L) {
     const Dims& d = c.d;
     StftArgs sa{wav, c.P[RTFS_P_WINDOW], c.P[RTFS_P_COSTAB], c.P[RTFS_P_SINTAB], c.buf(RTFS_WS_SPEC), L, d.T};
-    stft_kernel<<<dim3(d.T, d.B), 288, 0, c.st>>>(sa);
-    CK(cudaGetLastError());
-    CK(cudaMemsetAsync(c.stat(RTFS_ST_A0), 0, sizeof(double) * 2 * d.B, c.st));
+    {
+        STAGE(RTFS_SG_STFT);
+        stft_kernel<<<dim3(d.T, d.B), 288, 0, c.st>>>(sa);
+        CK(cudaGetLastError());
+    }
+    CKN(cudaMemsetAsync(c.stat(RTFS_ST_A0), 0, sizeof(double) * 2 * d.B, c.st));
     Im2colLoader al{c.buf(RTFS_WS_SPEC), d.T, d.F};
     StatsEpi ep{a0, 256, nullptr, c.stat(RTFS_ST_A0), (int)d.P, d.B};
+    STAGE(RTFS_SG_ENC_CONV);
     CK((launch_gemm<128, 32, true>(al, c.P[RTFS_P_ENC_W], ep, (int)(d.B * d.P), 256, c.st)));
     return 0;
 }
@@ -138,12 +183,13 @@ int run_encoder(const Ctx& c, const float* wav, float* a0, int L) {
 int run_bottleneck(const Ctx& c, const float* a0, float* a1, bool compute_stats) {
     const Dims& d = c.d;
     if (compute_stats) {
-        CK(cudaMemsetAsync(c.stat(RTFS_ST_A0), 0, sizeof(double) * 2 * d.B, c.st));
+        CKN(cudaMemsetAsync(c.stat(RTFS_ST_A0), 0, sizeof(double) * 2 * d.B, c.st));
         gln_stats_kernel<<<dim3(64, d.B), 256, 0, c.st>>>(a0, d.P * 256, c.stat(RTFS_ST_A0));
         CK(cudaGetLastError());
     }
     GlnActLoader<256, 1> al{a0, c.gln(RTFS_ST_A0, RTFS_P_BN_GAMMA, RTFS_P_BN_BETA, d.P * 256), (int)d.P, d.B};
     StoreEpi ep{a1, 256, c.P[RTFS_P_BN_B]};
+    STAGE(RTFS_SG_BOTTLENECK);
     CK((launch_gemm<128, 256, false>(al, c.P[RTFS_P_BN_W], ep, (int)(d.B * d.P), 256, c.st)));
     return 0;
 }
@@ -179,15 +225,22 @@ int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_f
     pa.time_path = which;
     pa.first = first ? 1 : 0;
     const long long npos = d.B * d.Pc;
-    dprnn_prep_kernel<<<(unsigned)((npos + 15) / 16), 256, 0, c.st>>>(pa);
-    CK(cudaGetLastError());
+    {
+        STAGE(RTFS_SG_DPRNN_PREP);
+        dprnn_prep_kernel<<<(unsigned)((npos + 15) / 16), 256, 0, c.st>>>(pa);
+        CK(cudaGetLastError());
+    }
     const float* resid = first ? g_first : g_in;
 
     // layer 0: unfold(8) + Linear(512 -> 256) as a GEMM over the overlapping row view of n
     {
         PlainLoader al{n, 64, 512};
         StoreEpi ep{U, 256, nullptr};
-        CK((launch_gemm<128, 512, false>(al, c.P[base + 2], ep, M, 256, c.st)));
+        {
+            STAGE(RTFS_SG_DPRNN_GEMM0);
+            CK((launch_gemm<128, 512, false>(al, c.P[base + 2], ep, M, 256, c.st)));
+        }
+        STAGE(RTFS_SG_DPRNN_SCAN);
         ScanArgs sa{U, 256, nullptr, c.P[base + 3], c.P[base + 4], hA, nseq, S, L, 4, S, 0, 0};
         sru_scan_kernel<<<(nseq + 3) / 4, 256, 0, c.st>>>(sa);
         CK(cudaGetLastError());
@@ -197,7 +250,11 @@ int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_f
         const int pw = base + 2 + 3 * l;
         PlainLoader al{hin, 64, 64};
         StoreEpi ep{U, 192, nullptr};
-        CK((launch_gemm<64, 64, false>(al, c.P[pw], ep, M, 192, c.st)));
+        {
+            STAGE(RTFS_SG_DPRNN_GEMML);
+            CK((launch_gemm<64, 64, false>(al, c.P[pw], ep, M, 192, c.st)));
+        }
+        STAGE(RTFS_SG_DPRNN_SCAN);
         const bool last = l == 3;
         float* hout = last ? hpad : (hin == hA ? hB : hA);
         ScanArgs sa{U, 192, hin, c.P[pw + 1], c.P[pw + 2], hout, nseq, S, L, 3, last ? S + 7 : S, last ? 7 : 0, last ? 1 : 0};
@@ -209,6 +266,7 @@ int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_f
     {
         PlainLoader al{hpad, 64, 512};
         ConvTEpi ep{g_out, resid, c.P[base + 15], S, n_other, which, d.Tc, d.Fc};
+        STAGE(RTFS_SG_DPRNN_CONVT);
         CK((launch_gemm<64, 512, false>(al, c.P[base + 14], ep, nseq * (S + 7), 64, c.st)));
     }
     return 0;
@@ -235,9 +293,10 @@ int run_mhsa(const Ctx& c, const float* g_in, float* g_out) {
         static bool cfg = false;
         const int smem = rowblock_smem_floats<96>() * 4;
         if (!cfg) {
-            CK(cudaFuncSetAttribute(rowblock_ln_kernel<96, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CKN(cudaFuncSetAttribute(rowblock_ln_kernel<96, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             cfg = true;
         }
+        STAGE(RTFS_SG_ATT_QKV);
         rowblock_ln_kernel<96, 0><<<d.B * d.Tc, 128, smem, c.st>>>(ra);
         CK(cudaGetLastError());
     }
@@ -255,9 +314,10 @@ int run_mhsa(const Ctx& c, const float* g_in, float* g_out) {
         if (smem > 227 * 1024) return fail_msg("attention: too many frames for the shared-memory score tile");
         static int cfg_smem = 0;
         if (smem > cfg_smem) {
-            CK(cudaFuncSetAttribute(attn_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CKN(cudaFuncSetAttribute(attn_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             cfg_smem = smem;
         }
+        STAGE(RTFS_SG_ATT_CORE);
         attn_core_kernel<<<dim3((d.Tc + AT_QT - 1) / AT_QT, d.B * H), 256, smem, c.st>>>(aa);
         CK(cudaGetLastError());
     }
@@ -278,9 +338,10 @@ int run_mhsa(const Ctx& c, const float* g_in, float* g_out) {
         static bool cfg = false;
         const int smem = rowblock_smem_floats<64>() * 4;
         if (!cfg) {
-            CK(cudaFuncSetAttribute(rowblock_ln_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CKN(cudaFuncSetAttribute(rowblock_ln_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             cfg = true;
         }
+        STAGE(RTFS_SG_ATT_PROJ);
         rowblock_ln_kernel<64, 1><<<d.B * d.Tc, 128, smem, c.st>>>(rb);
         CK(cudaGetLastError());
     }
@@ -299,23 +360,26 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out) {
     float *gec = c.buf(RTFS_WS_GEC), *ggc = c.buf(RTFS_WS_GGC);
     const int tseg_full = 32, tseg_comp = 16;
 
-    CK(cudaMemsetAsync(c.stat(RTFS_ST_PJ), 0, sizeof(double) * 2 * d.B * (RTFS_ST_COUNT - RTFS_ST_PJ), c.st));
+    CKN(cudaMemsetAsync(c.stat(RTFS_ST_PJ), 0, sizeof(double) * 2 * d.B * (RTFS_ST_COUNT - RTFS_ST_PJ), c.st));
     // S1 gateway + projection (+ gLN statistics)                         tdanet.py:34-49,107-108
     {
         GateLoader al{x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], 256};
         StatsEpi ep{p_pre, 64, P[RTFS_P_PJ_B], c.stat(RTFS_ST_PJ), (int)d.P, d.B};
+        STAGE(RTFS_SG_GATE_PROJ);
         CK((launch_gemm<64, 256, false>(al, P[RTFS_P_PJ_W], ep, M, 64, c.st)));
     }
     // S2 PReLU(gLN(p)) -> dw4x4 s1 -> d0_pre                              tdanet.py:61-68,113
     {
         XfGln<2> xf{p_pre, d.T, d.F, c.gln(RTFS_ST_PJ, RTFS_P_PJ_GAMMA, RTFS_P_PJ_BETA, nfull), P[RTFS_P_PJ_A]};
         DwArgs<1> a{d.T, d.F, d.T, d.F, tseg_full, {P[RTFS_P_D0_W]}, {P[RTFS_P_D0_B]}, {d0_pre}, {c.stat(RTFS_ST_D0)}, nullptr};
+        STAGE(RTFS_SG_DW_S1);
         CK((launch_dw<1, 4, 1, false>(xf, a, d.B, c.st)));
     }
     // S3 gLN(d0_pre) -> dw4x4 s2 -> d1_pre ; adaptive_avg_pool2d(d0) -> pool    tdanet.py:69-76,114-118
     {
         XfGln<0> xf{d0_pre, d.T, d.F, c.gln(RTFS_ST_D0, RTFS_P_D0_GAMMA, RTFS_P_D0_BETA, nfull), nullptr};
         DwArgs<1> a{d.T, d.F, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_D1_W]}, {P[RTFS_P_D1_B]}, {d1_pre}, {c.stat(RTFS_ST_D1)}, pool};
+        STAGE(RTFS_SG_DW_S2_POOL);
         CK((launch_dw<2, 2, 1, true>(xf, a, d.B, c.st)));
     }
     // S4-S9 global attention stack                                         tdanet.py:121
@@ -325,6 +389,7 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out) {
     // S10-S12 TF-AR units                                                  tdanet.py:124-129, layers/fusion.py:54-69
     {
         XfPlain xf{g3, d.Tc, d.Fc};
+        STAGE(RTFS_SG_TFAR_GLOBAL);
         DwArgs<2> a0{d.Tc, d.Fc, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_F0_EW], P[RTFS_P_F0_GW]}, {nullptr, nullptr}, {ge0, gg0}, {c.stat(RTFS_ST_F0E), c.stat(RTFS_ST_F0G)}, nullptr};
         CK((launch_dw<1, 2, 2, false>(xf, a0, d.B, c.st)));
         DwArgs<2> a1{d.Tc, d.Fc, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_F1_EW], P[RTFS_P_F1_GW]}, {nullptr, nullptr}, {ge1, gg1}, {c.stat(RTFS_ST_F1E), c.stat(RTFS_ST_F1G)}, nullptr};
@@ -333,11 +398,13 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out) {
     {
         XfGln<0> xf{d1_pre, d.Tc, d.Fc, c.gln(RTFS_ST_D1, RTFS_P_D1_GAMMA, RTFS_P_D1_BETA, ncomp), nullptr};
         DwArgs<1> a{d.Tc, d.Fc, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_F1_LW]}, {nullptr}, {le1}, {c.stat(RTFS_ST_F1L)}, nullptr};
+        STAGE(RTFS_SG_TFAR_GLOBAL);
         CK((launch_dw<1, 4, 1, false>(xf, a, d.B, c.st)));
     }
     {
         XfGln<0> xf{d0_pre, d.T, d.F, c.gln(RTFS_ST_D0, RTFS_P_D0_GAMMA, RTFS_P_D0_BETA, nfull), nullptr};
         DwArgs<1> a{d.T, d.F, d.T, d.F, tseg_full, {P[RTFS_P_F0_LW]}, {nullptr}, {le0}, {c.stat(RTFS_ST_F0L)}, nullptr};
+        STAGE(RTFS_SG_TFAR_LE0);
         CK((launch_dw<1, 4, 1, false>(xf, a, d.B, c.st)));
     }
     {
@@ -346,6 +413,7 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out) {
                   c.gln(RTFS_ST_F1L, RTFS_P_F1_LG, RTFS_P_F1_LB, ncomp), c.gln(RTFS_ST_F1G, RTFS_P_F1_GG, RTFS_P_F1_GB, ncomp),
                   c.gln(RTFS_ST_F1E, RTFS_P_F1_EG, RTFS_P_F1_EB, ncomp)};
         DwArgs<2> a{d.Tc, d.Fc, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_C0_EW], P[RTFS_P_C0_GW]}, {nullptr, nullptr}, {gec, ggc}, {c.stat(RTFS_ST_C0E), c.stat(RTFS_ST_C0G)}, nullptr};
+        STAGE(RTFS_SG_TFAR_CAT_GLOBAL);
         CK((launch_dw<1, 2, 2, false>(xf, a, d.B, c.st)));
     }
     {
@@ -354,6 +422,7 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out) {
                   c.gln(RTFS_ST_F0L, RTFS_P_F0_LG, RTFS_P_F0_LB, nfull), c.gln(RTFS_ST_F0G, RTFS_P_F0_GG, RTFS_P_F0_GB, ncomp),
                   c.gln(RTFS_ST_F0E, RTFS_P_F0_EG, RTFS_P_F0_EB, ncomp)};
         DwArgs<1> a{d.T, d.F, d.T, d.F, tseg_full, {P[RTFS_P_C0_LW]}, {nullptr}, {lec}, {c.stat(RTFS_ST_C0L)}, nullptr};
+        STAGE(RTFS_SG_TFAR_CAT_LOCAL);
         CK((launch_dw<1, 4, 1, false>(xf, a, d.B, c.st)));
     }
     // S13 e = TFAR_cat0(f0,f1) + d0 on the fly -> residual_conv + gateway(x) [+ addend]     tdanet.py:127-131
@@ -373,6 +442,7 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out) {
         al.Fc = d.Fc;
         al.B = d.B;
         ResidOutEpi ep{out, P[RTFS_P_RC_B], x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], addend, 0.f};
+        STAGE(RTFS_SG_RESID_OUT);
         CK((launch_gemm<128, 64, false>(al, P[RTFS_P_RC_W], ep, M, 256, c.st)));
     }
     return 0;
@@ -388,15 +458,19 @@ int run_caf(const Ctx& c, const float* audio, const float* video, const float* a
     if (smem > 200 * 1024) return fail_msg("CAF: too many video frames for the shared-memory softmax");
     static int cfg_smem = 48 * 1024;
     if (smem > cfg_smem) {
-        CK(cudaFuncSetAttribute(caf_video_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CKN(cudaFuncSetAttribute(caf_video_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         cfg_smem = smem;
     }
-    caf_video_kernel<<<d.B, 256, smem, c.st>>>(va);
-    CK(cudaGetLastError());
+    {
+        STAGE(RTFS_SG_CAF_VIDEO);
+        caf_video_kernel<<<d.B, 256, smem, c.st>>>(va);
+        CK(cudaGetLastError());
+    }
     CafApplyArgs aa{audio, addend, c.buf(RTFS_WS_VK), c.buf(RTFS_WS_ATT), P[RTFS_P_CAF_SK], P[RTFS_P_CAF_TK],
                     P[RTFS_P_CAF_SV], P[RTFS_P_CAF_TV], out, d.T, d.F, 256, d.Tv, d.B * d.P * 64};
     long long blocks = (aa.total4 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
+    STAGE(RTFS_SG_CAF_APPLY);
     caf_apply_kernel<<<(unsigned)blocks, 256, 0, c.st>>>(aa);
     CK(cudaGetLastError());
     return 0;
@@ -406,6 +480,7 @@ int run_mask(const Ctx& c, const float* refined, const float* a0, float* z) {
     const Dims& d = c.d;
     PreluLoader al{refined, c.P[RTFS_P_MK_A], 256};
     MaskEpi ep{z, c.P[RTFS_P_MK_B], a0};
+    STAGE(RTFS_SG_MASK);
     CK((launch_gemm<128, 256, false>(al, c.P[RTFS_P_MK_W], ep, (int)(d.B * d.P), 256, c.st)));
     return 0;
 }
@@ -414,8 +489,12 @@ int run_decoder(const Ctx& c, const float* z, float* wav_out, int L) {
     const Dims& d = c.d;
     PlainLoader al{z, 256, 256};
     StoreEpi ep{c.buf(RTFS_WS_Q18), 18, nullptr};
-    CK((launch_gemm<32, 256, true>(al, c.P[RTFS_P_DEC_W], ep, (int)(d.B * d.P), 18, c.st)));
+    {
+        STAGE(RTFS_SG_DEC_GEMM);
+        CK((launch_gemm<32, 256, true>(al, c.P[RTFS_P_DEC_W], ep, (int)(d.B * d.P), 18, c.st)));
+    }
     IstftArgs ia{c.buf(RTFS_WS_Q18), c.P[RTFS_P_WINDOW], c.P[RTFS_P_COSTAB], c.P[RTFS_P_SINTAB], wav_out, L, d.T};
+    STAGE(RTFS_SG_DEC_ISTFT);
     dec_istft_kernel<<<dim3((L + 127) / 128, d.B), 256, 0, c.st>>>(ia);
     CK(cudaGetLastError());
     return 0;
@@ -445,6 +524,31 @@ extern "C" {
 int rtfs_abi_version(void) { return RTFS_ABI_VERSION; }
 const char* rtfs_last_error(void) { return g_err.c_str(); }
 long long rtfs_last_launch_count(void) { return g_launches; }
+
+void rtfs_profile_enable(int on) {
+    g_prof.on = on != 0;
+    g_prof.used = 0;
+    g_prof.stage.clear();
+}
+
+int rtfs_profile_collect(float* ms, int* count) {
+    for (int i = 0; i < RTFS_SG_COUNT; ++i) {
+        ms[i] = 0.f;
+        count[i] = 0;
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return fail("cudaDeviceSynchronize", e);
+    for (size_t i = 0; i < g_prof.stage.size(); ++i) {
+        float t = 0.f;
+        e = cudaEventElapsedTime(&t, g_prof.pool[2 * i], g_prof.pool[2 * i + 1]);
+        if (e != cudaSuccess) return fail("cudaEventElapsedTime", e);
+        ms[g_prof.stage[i]] += t;
+        count[g_prof.stage[i]] += 1;
+    }
+    g_prof.used = 0;
+    g_prof.stage.clear();
+    return 0;
+}
 
 long long rtfs_ws_plan(int B, int L, int Tv, long long* offsets) {
     const Dims d = make_dims(B, L / 128 + 1, Tv);

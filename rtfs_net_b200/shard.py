@@ -61,7 +61,10 @@ def gather_outputs(local_out, n_items, rank, world):
     the serving path leaves each shard on its own GPU)."""
     if world == 1:
         return local_out
-    sizes = [shard_bounds(n_items, r, world) for r in range(world)]
-    bufs = [torch.empty((hi - lo,) + tuple(local_out.shape[1:]), dtype=local_out.dtype, device=local_out.device) for lo, hi in sizes]
-    dist.all_gather(bufs, local_out.contiguous())
-    return torch.cat(bufs, 0)
+    sizes = [hi - lo for lo, hi in (shard_bounds(n_items, r, world) for r in range(world))]
+    n_max = max(sizes)  # all_gather needs equal shapes: pad the short shards
+    padded = local_out.new_zeros((n_max,) + tuple(local_out.shape[1:]))
+    padded[: local_out.shape[0]] = local_out
+    bufs = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(bufs, padded)
+    return torch.cat([b[:n] for b, n in zip(bufs, sizes)], 0)
