@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RTFS_ABI_VERSION 1
+#define RTFS_ABI_VERSION 2
 #define RTFS_F 129
 #define RTFS_FC 64
 
@@ -68,6 +68,11 @@ enum rtfs_param {
     /* S3 mask + decoder */
     RTFS_P_MK_A, RTFS_P_MK_W, RTFS_P_MK_B, /* PReLU [1]; [256][256] tf32 rows interleaved (2c: real c, 2c+1: imag c+128); bias likewise */
     RTFS_P_DEC_W,                          /* [18][256]: row o*9+i*3+j = ConvTranspose2d weight[:, o, i, j] */
+    /* tcgen05 operand images of the GEMM weights above: W[N][K] (tf32) stored [K/4][N][4], i.e. every
+     * 32-wide K chunk is one contiguous N*128-byte slab in the UMMA K-major no-swizzle core-matrix layout */
+    RTFS_P_BN_WI, RTFS_P_PJ_WI, RTFS_P_RC_WI, RTFS_P_MK_WI,
+    RTFS_P_RF_WI0, RTFS_P_RF_WI1, RTFS_P_RF_WI2, RTFS_P_RF_WI3, RTFS_P_RF_CTWI,
+    RTFS_P_RT_WI0, RTFS_P_RT_WI1, RTFS_P_RT_WI2, RTFS_P_RT_WI3, RTFS_P_RT_CTWI,
     RTFS_P_COUNT
 };
 

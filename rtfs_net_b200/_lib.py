@@ -71,6 +71,7 @@ P = {n: i for i, n in enumerate(PARAM_NAMES)}
 WS = {n: i for i, n in enumerate(WS_NAMES)}
 ST = {n: i for i, n in enumerate(STAT_NAMES)}
 
+ABI_VERSION = 2
 _lib = None
 
 
@@ -88,7 +89,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if handle.rtfs_abi_version() != 1:
+        if handle.rtfs_abi_version() != ABI_VERSION:
             raise RuntimeError("librtfs_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -12,12 +12,24 @@
 #include "dwconv.cuh"
 #include "frontend.cuh"
 #include "gemm.cuh"
+#include "gemm_tc.cuh"
 
 using namespace rtfs;
 
 namespace {
 
 thread_local std::string g_err;
+
+// Kernel generation switches (debug / A-B measurement): RTFS_LEGACY_GEMM=1 routes every contraction
+// through the mma.sync kernels of gemm.cuh instead of the tcgen05 kernels of gemm_tc.cuh.
+bool env_flag(const char* name) {
+    const char* v = getenv(name);
+    return v != nullptr && v[0] != '\0' && v[0] != '0';
+}
+bool use_tc() {
+    static const bool v = !env_flag("RTFS_LEGACY_GEMM");
+    return v;
+}
 thread_local long long g_launches = 0;
 
 // Optional per-stage device timing (bench.py roofline leg): cudaEvent pairs recorded on the launch
@@ -188,9 +200,14 @@ int run_bottleneck(const Ctx& c, const float* a0, float* a1, bool compute_stats)
         CK(cudaGetLastError());
     }
     GlnActLoader<256, 1> al{a0, c.gln(RTFS_ST_A0, RTFS_P_BN_GAMMA, RTFS_P_BN_BETA, d.P * 256), (int)d.P, d.B};
-    StoreEpi ep{a1, 256, c.P[RTFS_P_BN_B]};
     STAGE(RTFS_SG_BOTTLENECK);
-    CK((launch_gemm<128, 256, false>(al, c.P[RTFS_P_BN_W], ep, (int)(d.B * d.P), 256, c.st)));
+    if (use_tc()) {
+        StoreEpi4 ep{a1, 256, c.P[RTFS_P_BN_B]};
+        CK((launch_gemm_tc<256, 256, 3, 1>(al, c.P[RTFS_P_BN_WI], ep, (int)(d.B * d.P), c.st)));
+    } else {
+        StoreEpi ep{a1, 256, c.P[RTFS_P_BN_B]};
+        CK((launch_gemm<128, 256, false>(al, c.P[RTFS_P_BN_W], ep, (int)(d.B * d.P), 256, c.st)));
+    }
     return 0;
 }
 
@@ -198,6 +215,7 @@ int run_bottleneck(const Ctx& c, const float* a0, float* a1, bool compute_stats)
 int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_first, float* g_out) {
     const Dims& d = c.d;
     const int base = which == 0 ? RTFS_P_RF_LNG : RTFS_P_RT_LNG;
+    const int basei = which == 0 ? RTFS_P_RF_WI0 : RTFS_P_RT_WI0;
     const int S = which == 0 ? d.Fc : d.Tc;
     const int n_other = which == 0 ? d.Tc : d.Fc;
     const int nseq = d.B * n_other;
@@ -235,10 +253,15 @@ int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_f
     // layer 0: unfold(8) + Linear(512 -> 256) as a GEMM over the overlapping row view of n
     {
         PlainLoader al{n, 64, 512};
-        StoreEpi ep{U, 256, nullptr};
         {
             STAGE(RTFS_SG_DPRNN_GEMM0);
-            CK((launch_gemm<128, 512, false>(al, c.P[base + 2], ep, M, 256, c.st)));
+            if (use_tc()) {
+                StoreEpi4 ep{U, 256, nullptr};
+                CK((launch_gemm_tc<256, 512, 3, 1>(al, c.P[basei + 0], ep, M, c.st)));
+            } else {
+                StoreEpi ep{U, 256, nullptr};
+                CK((launch_gemm<128, 512, false>(al, c.P[base + 2], ep, M, 256, c.st)));
+            }
         }
         STAGE(RTFS_SG_DPRNN_SCAN);
         ScanArgs sa{U, 256, nullptr, c.P[base + 3], c.P[base + 4], hA, nseq, S, L, 4, S, 0, 0};
@@ -249,10 +272,15 @@ int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_f
     for (int l = 1; l <= 3; ++l) {
         const int pw = base + 2 + 3 * l;
         PlainLoader al{hin, 64, 64};
-        StoreEpi ep{U, 192, nullptr};
         {
             STAGE(RTFS_SG_DPRNN_GEMML);
-            CK((launch_gemm<64, 64, false>(al, c.P[pw], ep, M, 192, c.st)));
+            if (use_tc()) {
+                StoreEpi4 ep{U, 192, nullptr};
+                CK((launch_gemm_tc<192, 64, 2, 2>(al, c.P[basei + l], ep, M, c.st)));
+            } else {
+                StoreEpi ep{U, 192, nullptr};
+                CK((launch_gemm<64, 64, false>(al, c.P[pw], ep, M, 192, c.st)));
+            }
         }
         STAGE(RTFS_SG_DPRNN_SCAN);
         const bool last = l == 3;
@@ -265,9 +293,14 @@ int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_f
     // ConvTranspose1d(64,64,8) + bias + residual as a GEMM over the overlapping view of the padded h
     {
         PlainLoader al{hpad, 64, 512};
-        ConvTEpi ep{g_out, resid, c.P[base + 15], S, n_other, which, d.Tc, d.Fc};
         STAGE(RTFS_SG_DPRNN_CONVT);
-        CK((launch_gemm<64, 512, false>(al, c.P[base + 14], ep, nseq * (S + 7), 64, c.st)));
+        if (use_tc()) {
+            ConvTEpi4 ep{g_out, resid, c.P[base + 15], S, n_other, which, d.Tc, d.Fc};
+            CK((launch_gemm_tc<64, 512, 4, 2>(al, c.P[basei + 4], ep, nseq * (S + 7), c.st)));
+        } else {
+            ConvTEpi ep{g_out, resid, c.P[base + 15], S, n_other, which, d.Tc, d.Fc};
+            CK((launch_gemm<64, 512, false>(al, c.P[base + 14], ep, nseq * (S + 7), 64, c.st)));
+        }
     }
     return 0;
 }
@@ -364,9 +397,14 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out) {
     // S1 gateway + projection (+ gLN statistics)                         tdanet.py:34-49,107-108
     {
         GateLoader al{x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], 256};
-        StatsEpi ep{p_pre, 64, P[RTFS_P_PJ_B], c.stat(RTFS_ST_PJ), (int)d.P, d.B};
         STAGE(RTFS_SG_GATE_PROJ);
-        CK((launch_gemm<64, 256, false>(al, P[RTFS_P_PJ_W], ep, M, 64, c.st)));
+        if (use_tc()) {
+            StatsEpi4 ep{p_pre, 64, P[RTFS_P_PJ_B], c.stat(RTFS_ST_PJ), (int)d.P, d.B};
+            CK((launch_gemm_tc<64, 256, 4, 2>(al, P[RTFS_P_PJ_WI], ep, M, c.st)));
+        } else {
+            StatsEpi ep{p_pre, 64, P[RTFS_P_PJ_B], c.stat(RTFS_ST_PJ), (int)d.P, d.B};
+            CK((launch_gemm<64, 256, false>(al, P[RTFS_P_PJ_W], ep, M, 64, c.st)));
+        }
     }
     // S2 PReLU(gLN(p)) -> dw4x4 s1 -> d0_pre                              tdanet.py:61-68,113
     {
@@ -441,9 +479,14 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out) {
         al.Tc = d.Tc;
         al.Fc = d.Fc;
         al.B = d.B;
-        ResidOutEpi ep{out, P[RTFS_P_RC_B], x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], addend, 0.f};
         STAGE(RTFS_SG_RESID_OUT);
-        CK((launch_gemm<128, 64, false>(al, P[RTFS_P_RC_W], ep, M, 256, c.st)));
+        if (use_tc()) {
+            ResidOutEpi4 ep{out, P[RTFS_P_RC_B], x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], addend, 0.f};
+            CK((launch_gemm_tc<256, 64, 2, 2>(al, P[RTFS_P_RC_WI], ep, M, c.st)));
+        } else {
+            ResidOutEpi ep{out, P[RTFS_P_RC_B], x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], addend, 0.f};
+            CK((launch_gemm<128, 64, false>(al, P[RTFS_P_RC_W], ep, M, 256, c.st)));
+        }
     }
     return 0;
 }
@@ -479,9 +522,14 @@ int run_caf(const Ctx& c, const float* audio, const float* video, const float* a
 int run_mask(const Ctx& c, const float* refined, const float* a0, float* z) {
     const Dims& d = c.d;
     PreluLoader al{refined, c.P[RTFS_P_MK_A], 256};
-    MaskEpi ep{z, c.P[RTFS_P_MK_B], a0};
     STAGE(RTFS_SG_MASK);
-    CK((launch_gemm<128, 256, false>(al, c.P[RTFS_P_MK_W], ep, (int)(d.B * d.P), 256, c.st)));
+    if (use_tc()) {
+        MaskEpi4 ep{z, c.P[RTFS_P_MK_B], a0};
+        CK((launch_gemm_tc<256, 256, 3, 1>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
+    } else {
+        MaskEpi ep{z, c.P[RTFS_P_MK_B], a0};
+        CK((launch_gemm<128, 256, false>(al, c.P[RTFS_P_MK_W], ep, (int)(d.B * d.P), 256, c.st)));
+    }
     return 0;
 }
 

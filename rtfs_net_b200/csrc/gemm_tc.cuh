@@ -1,0 +1,385 @@
+// tcgen05 (5th-gen tensor core) row-tile GEMM for the dense contractions of the RTFS-Net forward:
+//     C[M x BN] = f(A)[M x KTOT] * W[BN x KTOT]^T        (fp32 in HBM, TF32 operands, fp32 accumulate in TMEM)
+// One CTA = one 128-row tile.  K is streamed in chunks of 32 through an NS-stage shared-memory ring:
+//   * A chunk: produced by the same loader functors as the legacy kernel (gemm.cuh: fused gLN-apply /
+//     PReLU / gateway / TF-AR combine ...), rounded to TF32 (cvt.rna) and written by all 256 threads in
+//     the UMMA canonical K-major no-swizzle layout (8-row x 16-byte core matrices):
+//         byte(r, k) = (k/4) * LBO_A + r*16 + (k%4)*4 ,  LBO_A = 128*16 + 16 (pad: conflict-free STS.128), SBO = 128
+//   * W chunk: a contiguous BN*128-byte slab of the host-prepared image Wimg[K/4][BN][4], fetched with one
+//     cp.async.bulk (TMA engine, mbarrier complete_tx) -- LBO_B = BN*16, SBO = 128.
+//   * thread 0 issues 4 x tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per chunk and commits to the stage's
+//     mbarrier; MMAs run asynchronously while the CTA stages the following chunks.
+// Epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> per-warp shared-memory transpose -> the epilogue
+// functor sees float4 pieces of rows, so every global access of the epilogue is a coalesced 128-byte row
+// segment (bias / residual / gateway recompute / complex mask / gLN statistics fused as before).
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace rtfs {
+
+// ---------------------------------------------------------------------------------- PTX wrappers
+DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded spin: a protocol bug traps instead of hanging the device.
+DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+// TMA engine bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+DEVINL void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+DEVINL void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int NCOLS>
+DEVINL void tmem_alloc(uint32_t* slot) {  // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"((uint32_t)NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+DEVINL void tmem_dealloc(uint32_t taddr) {  // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"((uint32_t)NCOLS) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, TF32 inputs, fp32 accumulate; issued by ONE thread
+DEVINL void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrive once all tcgen05 ops issued so far by this thread have completed
+DEVINL void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets TMEM lane (lane_base + i)
+DEVINL void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor, version 1):
+//   [0,14) start>>4 | [16,30) leading (K-direction core-matrix) byte offset>>4 | [32,46) stride (8-row group) byte offset>>4
+DEVINL uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, TF32 x TF32, both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------- float4 epilogues
+// contract: init(row0, M) ; store4(row, col, v) for columns col..col+3 of an in-range row ; finish(scratch)
+DEVINL float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+struct StoreEpi4 {
+    float* C;
+    long long ldc;
+    const float* bias;  // may be null
+    DEVINL void init(int, int) {}
+    DEVINL void store4(int row, int col, float4 v) {
+        if (bias) v = add4(v, ldg4(bias + col));
+        *reinterpret_cast<float4*>(C + (long long)row * ldc + col) = v;
+    }
+    DEVINL void finish(float*) {}
+};
+
+struct StatsEpi4 {
+    float* C;
+    long long ldc;
+    const float* bias;
+    double* sums;  // [B][2]
+    int P, B;
+    int bfirst_, split_;
+    float s0_, q0_, s1_, q1_;
+    DEVINL void init(int row0, int) {
+        bfirst_ = row0 / P;
+        split_ = (bfirst_ + 1) * P;
+        s0_ = q0_ = s1_ = q1_ = 0.f;
+    }
+    DEVINL void store4(int row, int col, float4 v) {
+        if (bias) v = add4(v, ldg4(bias + col));
+        *reinterpret_cast<float4*>(C + (long long)row * ldc + col) = v;
+        const float s = (v.x + v.y) + (v.z + v.w);
+        const float q = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        if (row < split_) {
+            s0_ += s;
+            q0_ += q;
+        } else {
+            s1_ += s;
+            q1_ += q;
+        }
+    }
+    DEVINL void finish(float* scratch) {
+        block_stats_atomic(s0_, q0_, sums + 2 * bfirst_, scratch);
+        block_stats_atomic(s1_, q1_, (bfirst_ + 1 < B) ? sums + 2 * (bfirst_ + 1) : nullptr, scratch);
+    }
+};
+
+// residual_conv epilogue (tdanet.py:131): out = acc + bias + gateway(x) [+ a1 -> next block input]
+struct ResidOutEpi4 {
+    float* out;
+    const float* bias;
+    const float* x;
+    const float* wg;
+    const float* bg;
+    const float* slope;
+    const float* a1;  // may be null
+    float a_;
+    DEVINL void init(int, int) { a_ = __ldg(slope); }
+    DEVINL void store4(int row, int col, float4 v) {
+        const long long o = (long long)row * 256 + col;
+        const float4 xx = ldg4(x + o), w = ldg4(wg + col), b = ldg4(bg + col), bi = ldg4(bias + col);
+        v.x += bi.x + prelu(fmaf(w.x, xx.x, b.x), a_);
+        v.y += bi.y + prelu(fmaf(w.y, xx.y, b.y), a_);
+        v.z += bi.z + prelu(fmaf(w.z, xx.z, b.z), a_);
+        v.w += bi.w + prelu(fmaf(w.w, xx.w, b.w), a_);
+        if (a1) v = add4(v, ldg4(a1 + o));
+        *reinterpret_cast<float4*>(out + o) = v;
+    }
+    DEVINL void finish(float*) {}
+};
+
+// S^3 mask epilogue (mask_generator.py:67-99); GEMM columns interleaved on the host: col 2c = real-half
+// channel c, col 2c+1 = imag-half channel c+128 -> a float4 holds (re c, im c, re c+1, im c+1).
+struct MaskEpi4 {
+    float* z;
+    const float* bias;
+    const float* a0;
+    DEVINL void init(int, int) {}
+    DEVINL void store4(int row, int col, float4 v) {
+        const float4 bi = ldg4(bias + col);
+        const float mr0 = fmaxf(v.x + bi.x, 0.f), mi0 = fmaxf(v.y + bi.y, 0.f);
+        const float mr1 = fmaxf(v.z + bi.z, 0.f), mi1 = fmaxf(v.w + bi.w, 0.f);
+        const long long o = (long long)row * 256 + (col >> 1);
+        const float2 er = ldg2(a0 + o), ei = ldg2(a0 + o + 128);
+        *reinterpret_cast<float2*>(z + o) = make_float2(er.x * mr0 - ei.x * mi0, er.y * mr1 - ei.y * mi1);
+        *reinterpret_cast<float2*>(z + o + 128) = make_float2(er.x * mi0 + ei.x * mr0, er.y * mi1 + ei.y * mr1);
+    }
+    DEVINL void finish(float*) {}
+};
+
+// ConvTranspose1d-as-GEMM epilogue of the dual-path RNN (rnn_layers.py:153-160)
+struct ConvTEpi4 {
+    float* out;
+    const float* resid;
+    const float* bias;
+    int S, n_other, time_path, Tc, Fc;
+    DEVINL void init(int, int) {}
+    DEVINL void store4(int row, int col, float4 v) {
+        const int seq = row / (S + 7), s = row - seq * (S + 7);
+        if (s >= S) return;
+        const int b = seq / n_other, o = seq - b * n_other;
+        const int t = time_path ? s : o, f = time_path ? o : s;
+        const long long off = ((((long long)b * Tc + t) * Fc) + f) * 64 + col;
+        v = add4(add4(v, ldg4(bias + col)), ldg4(resid + off));
+        *reinterpret_cast<float4*>(out + off) = v;
+    }
+    DEVINL void finish(float*) {}
+};
+
+// ---------------------------------------------------------------------------------- kernel
+constexpr int TC_BM = 128, TC_KC = 32, TC_THREADS = 256;
+constexpr int TC_LBO_A = TC_BM * 16 + 16;              // 2064 B between K-direction core matrices of A
+constexpr int TC_A_STAGE = 16640;                      // 8 * 2064 = 16512, rounded up to 128
+constexpr int TC_STG_LD = 36;                          // floats per staged epilogue row (32 + 4 pad)
+constexpr int TC_STG_BYTES = 8 * 32 * TC_STG_LD * 4;   // 8 warps x [32][36] floats
+
+template <int BN>
+__host__ __device__ constexpr int tc_tmem_cols() {
+    return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+}
+template <int BN, int NS>
+__host__ __device__ constexpr int tc_stage_bytes() {
+    return NS * (TC_A_STAGE + BN * 128);
+}
+template <int BN, int NS>
+__host__ __device__ constexpr int tc_smem_bytes(int extra_floats) {
+    return (tc_stage_bytes<BN, NS>() > TC_STG_BYTES ? tc_stage_bytes<BN, NS>() : TC_STG_BYTES) + extra_floats * 4 + 256 + 128;
+}
+
+template <int BN, int KTOT, int NS, int MINB, class AL, class EP>
+__global__ void __launch_bounds__(TC_THREADS, MINB) gemm_tc_kernel(AL al, const float* __restrict__ Wimg, EP ep, int M) {
+    constexpr int NK = KTOT / TC_KC;
+    constexpr int WBYTES = BN * 128;
+    constexpr int TCOLS = tc_tmem_cols<BN>();
+    constexpr int PD = (NK <= NS) ? NK : NS - 2;  // W chunks in flight ahead of the A producer
+    static_assert(KTOT % TC_KC == 0, "K must be a multiple of 32");
+    static_assert(BN % 64 == 0 && BN <= 256, "N must be 64, 128, 192 or 256");
+    static_assert(NK <= NS || NS >= 3, "a ring shorter than K needs >= 3 stages");
+    constexpr int STAGE_AREA = tc_stage_bytes<BN, NS>() > TC_STG_BYTES ? tc_stage_bytes<BN, NS>() : TC_STG_BYTES;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* a_stage = smem_raw;
+    unsigned char* w_stage = smem_raw + NS * TC_A_STAGE;
+    float* extra = reinterpret_cast<float*>(smem_raw + STAGE_AREA);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + STAGE_AREA + AL::kExtra * 4);  // full_w[NS] | mma_done[NS]
+    uint64_t* full_w = bars;
+    uint64_t* mma_done = bars + NS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS);
+    float* scratch = reinterpret_cast<float*>(tmem_slot + 4);  // 16 floats for block_stats_atomic
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row0 = blockIdx.x * TC_BM;
+
+    if (warp == 0) tmem_alloc<TCOLS>(tmem_slot);
+    if (tid == 32) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(full_w + s, 1);
+            mbar_init(mma_done + s, 1);
+        }
+        fence_mbar_init();
+    }
+    al.init(row0, M, extra);
+    ep.init(row0, M);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    auto issue_w = [&](int c) {  // thread 0 only
+        const int s = c % NS;
+        mbar_expect_tx(full_w + s, WBYTES);
+        bulk_g2s(w_stage + (size_t)s * WBYTES, Wimg + (size_t)c * (BN * TC_KC), WBYTES, full_w + s);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int c = 0; c < PD && c < NK; ++c) issue_w(c);
+    }
+
+    // thread (tid>>3)+32i owns row r_i of the tile, 16-byte K piece (tid&7) of every chunk
+    const int kq = tid & 7;
+    unsigned char* a_dst0 = a_stage + kq * TC_LBO_A + (tid >> 3) * 16;
+    constexpr uint32_t IDESC = umma_idesc_tf32(TC_BM, BN);
+
+    float4 areg[2][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) areg[0][i] = al.load(i, kq * 4);
+    if (NK > 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) areg[1][i] = al.load(i, TC_KC + kq * 4);
+    }
+
+#pragma unroll
+    for (int kc = 0; kc < NK; ++kc) {
+        const int s = kc % NS;
+        if (kc >= NS) mbar_wait(mma_done + s, ((kc / NS) - 1) & 1);  // MMAs of chunk kc-NS have read this stage
+        if (NK > NS && tid == 0 && kc + PD < NK) {
+            const int c = kc + PD;  // its stage was last read by chunk c-NS = kc-2
+            if (c >= NS) mbar_wait(mma_done + (c % NS), ((c / NS) - 1) & 1);
+            issue_w(c);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float4 v = areg[kc & 1][i];
+            v.x = tf32r(v.x);
+            v.y = tf32r(v.y);
+            v.z = tf32r(v.z);
+            v.w = tf32r(v.w);
+            *reinterpret_cast<float4*>(a_dst0 + (size_t)s * TC_A_STAGE + i * (32 * 16)) = v;
+        }
+        if (kc + 2 < NK) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) areg[kc & 1][i] = al.load(i, (kc + 2) * TC_KC + kq * 4);
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+        __syncthreads();
+        if (tid == 0) {
+            mbar_wait(full_w + s, (kc / NS) & 1);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(a_stage + (size_t)s * TC_A_STAGE);
+            const uint32_t w_base = smem_u32(w_stage + (size_t)s * WBYTES);
+#pragma unroll
+            for (int q = 0; q < TC_KC / 8; ++q) {
+                const uint64_t da = umma_desc(a_base + 2 * q * TC_LBO_A, TC_LBO_A, 128);
+                const uint64_t db = umma_desc(w_base + 2 * q * (BN * 16), BN * 16, 128);
+                umma_tf32(tmem, da, db, IDESC, (kc > 0 || q > 0) ? 1u : 0u);
+            }
+            umma_commit(mma_done + s);
+        }
+    }
+    // accumulator complete once the last chunk's commit has arrived (commits complete in order)
+    mbar_wait(mma_done + ((NK - 1) % NS), ((NK - 1) / NS) & 1);
+    tc_fence_after();
+
+    // ---- epilogue: warp w reads TMEM lanes 32*(w&3).. (rows), column half (w>>2)
+    {
+        const int q = warp & 3, hlf = warp >> 2;
+        float* stg = reinterpret_cast<float*>(smem_raw) + warp * (32 * TC_STG_LD);
+        const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll 1
+        for (int cb = 0; cb < BN / 64; ++cb) {
+            const int col0 = hlf * (BN / 2) + cb * 32;
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(stg + lane * TC_STG_LD + 4 * i) =
+                    make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            __syncwarp();
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const int r = p * 4 + rsub;
+                const float4 x = *reinterpret_cast<const float4*>(stg + r * TC_STG_LD + c4);
+                const int row = row0 + q * 32 + r;
+                if (row < M) ep.store4(row, col0 + c4, x);
+            }
+            __syncwarp();
+        }
+    }
+    ep.finish(scratch);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<TCOLS>(tmem);
+}
+
+template <int BN, int KTOT, int NS, int MINB, class AL, class EP>
+inline cudaError_t launch_gemm_tc(const AL& al, const float* Wimg, const EP& ep, int M, cudaStream_t st) {
+    auto kern = gemm_tc_kernel<BN, KTOT, NS, MINB, AL, EP>;
+    const int smem = tc_smem_bytes<BN, NS>(AL::kExtra);
+    static bool configured = false;  // one flag per instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<(M + TC_BM - 1) / TC_BM, TC_THREADS, smem, st>>>(al, Wimg, ep, M);
+    return cudaGetLastError();
+}
+
+}  // namespace rtfs

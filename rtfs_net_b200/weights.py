@@ -24,6 +24,14 @@ def tf32_round(x: torch.Tensor) -> torch.Tensor:
     return i.view(torch.float32)
 
 
+def umma_image(w: torch.Tensor) -> torch.Tensor:
+    """W[N][K] -> [K/4][N][4]: the tcgen05 K-major no-swizzle operand image (gemm_tc.cuh); each 32-wide
+    K chunk is then one contiguous N*128-byte slab a single bulk copy drops into shared memory."""
+    N, K = w.shape
+    assert K % 32 == 0
+    return w.reshape(N, K // 4, 4).permute(1, 0, 2).contiguous()
+
+
 def _tapmajor(w):
     """depthwise (C,1,4,4) -> [16][C]"""
     C = w.shape[0]
@@ -140,6 +148,13 @@ def prepare(sd, device):
     out["RTFS_P_MK_W"] = tf32_round(g("mask_generator.mask_generator.1.full_layer.2.weight").reshape(256, 256)[perm])
     out["RTFS_P_MK_B"] = g("mask_generator.mask_generator.1.full_layer.2.bias")[perm].contiguous()
     out["RTFS_P_DEC_W"] = g("decoder.decoder.weight").permute(1, 2, 3, 0).reshape(18, 256).contiguous()
+
+    for src, dst in (("BN_W", "BN_WI"), ("PJ_W", "PJ_WI"), ("RC_W", "RC_WI"), ("MK_W", "MK_WI")):
+        out["RTFS_P_" + dst] = umma_image(out["RTFS_P_" + src])
+    for tag in ("RF", "RT"):
+        for l in range(4):
+            out[f"RTFS_P_{tag}_WI{l}"] = umma_image(out[f"RTFS_P_{tag}_W{l}"])
+        out[f"RTFS_P_{tag}_CTWI"] = umma_image(out[f"RTFS_P_{tag}_CTW"])
 
     missing = [n for n in _lib.PARAM_NAMES if n not in out]
     if missing:

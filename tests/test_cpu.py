@@ -198,7 +198,7 @@ def test_library_exports_every_declared_symbol():
     handle = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(handle, name), name
-    assert _lib.lib().rtfs_abi_version() == 1
+    assert _lib.lib().rtfs_abi_version() == _lib.ABI_VERSION
 
 
 def test_workspace_plan_is_consistent():

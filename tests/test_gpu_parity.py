@@ -58,7 +58,7 @@ def ws_view(model, name, shape):
 def test_library_loaded():
     from rtfs_net_b200 import _lib
 
-    assert _lib.lib().rtfs_abi_version() == 1
+    assert _lib.lib().rtfs_abi_version() == _lib.ABI_VERSION
 
 
 def test_encoder(model, golden_sd, O):
