@@ -10,6 +10,7 @@
 #include "caf.cuh"
 #include "dprnn.cuh"
 #include "dwconv.cuh"
+#include "dwroll.cuh"
 #include "frontend.cuh"
 #include "gemm.cuh"
 #include "gemm_tc.cuh"
@@ -25,6 +26,10 @@ thread_local std::string g_err;
 bool env_flag(const char* name) {
     const char* v = getenv(name);
     return v != nullptr && v[0] != '\0' && v[0] != '0';
+}
+bool use_roll() {  // RTFS_LEGACY_DW=1: first-generation depthwise kernels (dwconv.cuh)
+    static const bool v = !env_flag("RTFS_LEGACY_DW");
+    return v;
 }
 bool use_tc() {
     static const bool v = !env_flag("RTFS_LEGACY_GEMM");
@@ -406,62 +411,134 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out) {
             CK((launch_gemm<64, 256, false>(al, P[RTFS_P_PJ_W], ep, M, 64, c.st)));
         }
     }
-    // S2 PReLU(gLN(p)) -> dw4x4 s1 -> d0_pre                              tdanet.py:61-68,113
-    {
-        XfGln<2> xf{p_pre, d.T, d.F, c.gln(RTFS_ST_PJ, RTFS_P_PJ_GAMMA, RTFS_P_PJ_BETA, nfull), P[RTFS_P_PJ_A]};
-        DwArgs<1> a{d.T, d.F, d.T, d.F, tseg_full, {P[RTFS_P_D0_W]}, {P[RTFS_P_D0_B]}, {d0_pre}, {c.stat(RTFS_ST_D0)}, nullptr};
-        STAGE(RTFS_SG_DW_S1);
-        CK((launch_dw<1, 4, 1, false>(xf, a, d.B, c.st)));
-    }
-    // S3 gLN(d0_pre) -> dw4x4 s2 -> d1_pre ; adaptive_avg_pool2d(d0) -> pool    tdanet.py:69-76,114-118
-    {
-        XfGln<0> xf{d0_pre, d.T, d.F, c.gln(RTFS_ST_D0, RTFS_P_D0_GAMMA, RTFS_P_D0_BETA, nfull), nullptr};
-        DwArgs<1> a{d.T, d.F, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_D1_W]}, {P[RTFS_P_D1_B]}, {d1_pre}, {c.stat(RTFS_ST_D1)}, pool};
-        STAGE(RTFS_SG_DW_S2_POOL);
-        CK((launch_dw<2, 2, 1, true>(xf, a, d.B, c.st)));
+    const bool roll = use_roll();
+    if (roll) {
+        // S2 PReLU(gLN(p)) -> dw4x4 s1 -> d0_pre                              tdanet.py:61-68,113
+        {
+            XrGln<2> xf{p_pre, d.T, d.F, c.gln(RTFS_ST_PJ, RTFS_P_PJ_GAMMA, RTFS_P_PJ_BETA, nfull), P[RTFS_P_PJ_A]};
+            DrArgs<1> a{};
+            a.Ti = d.T; a.Fi = d.F;
+            a.w[0] = P[RTFS_P_D0_W]; a.bias[0] = P[RTFS_P_D0_B]; a.out[0] = d0_pre; a.sums[0] = c.stat(RTFS_ST_D0);
+            STAGE(RTFS_SG_DW_S1);
+            CK((launch_dwroll<XrGln<2>, 1, false, 288>(xf, a, d.B, c.st)));
+        }
+        // S3 one pass over gLN(d0_pre): local conv of fusion_layers.0 (le0), dw4x4 s2 (d1_pre), adaptive pool
+        //                                                            tdanet.py:69-76,114-118 ; layers/fusion.py:56
+        {
+            XrGln<0> xf{d0_pre, d.T, d.F, c.gln(RTFS_ST_D0, RTFS_P_D0_GAMMA, RTFS_P_D0_BETA, nfull), nullptr};
+            DrArgs<1> a{};
+            a.Ti = d.T; a.Fi = d.F;
+            a.w[0] = P[RTFS_P_F0_LW]; a.bias[0] = nullptr; a.out[0] = le0; a.sums[0] = c.stat(RTFS_ST_F0L);
+            a.w2 = P[RTFS_P_D1_W]; a.bias2 = P[RTFS_P_D1_B]; a.out2 = d1_pre; a.sums2 = c.stat(RTFS_ST_D1);
+            a.pool = pool; a.To2 = d.Tc; a.Fo2 = d.Fc;
+            STAGE(RTFS_SG_DW_S2_POOL);
+            CK((launch_dwroll<XrGln<0>, 1, true, 288>(xf, a, d.B, c.st)));
+        }
+    } else {
+        // S2 PReLU(gLN(p)) -> dw4x4 s1 -> d0_pre                              tdanet.py:61-68,113
+        {
+            XfGln<2> xf{p_pre, d.T, d.F, c.gln(RTFS_ST_PJ, RTFS_P_PJ_GAMMA, RTFS_P_PJ_BETA, nfull), P[RTFS_P_PJ_A]};
+            DwArgs<1> a{d.T, d.F, d.T, d.F, tseg_full, {P[RTFS_P_D0_W]}, {P[RTFS_P_D0_B]}, {d0_pre}, {c.stat(RTFS_ST_D0)}, nullptr};
+            STAGE(RTFS_SG_DW_S1);
+            CK((launch_dw<1, 4, 1, false>(xf, a, d.B, c.st)));
+        }
+        // S3 gLN(d0_pre) -> dw4x4 s2 -> d1_pre ; adaptive_avg_pool2d(d0) -> pool    tdanet.py:69-76,114-118
+        {
+            XfGln<0> xf{d0_pre, d.T, d.F, c.gln(RTFS_ST_D0, RTFS_P_D0_GAMMA, RTFS_P_D0_BETA, nfull), nullptr};
+            DwArgs<1> a{d.T, d.F, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_D1_W]}, {P[RTFS_P_D1_B]}, {d1_pre}, {c.stat(RTFS_ST_D1)}, pool};
+            STAGE(RTFS_SG_DW_S2_POOL);
+            CK((launch_dw<2, 2, 1, true>(xf, a, d.B, c.st)));
+        }
     }
     // S4-S9 global attention stack                                         tdanet.py:121
     RUN(run_dprnn(c, 0, true, nullptr, g0, g1));
     RUN(run_dprnn(c, 1, false, g1, nullptr, g2));
     RUN(run_mhsa(c, g2, g3));
-    // S10-S12 TF-AR units                                                  tdanet.py:124-129, layers/fusion.py:54-69
-    {
-        XfPlain xf{g3, d.Tc, d.Fc};
-        STAGE(RTFS_SG_TFAR_GLOBAL);
-        DwArgs<2> a0{d.Tc, d.Fc, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_F0_EW], P[RTFS_P_F0_GW]}, {nullptr, nullptr}, {ge0, gg0}, {c.stat(RTFS_ST_F0E), c.stat(RTFS_ST_F0G)}, nullptr};
-        CK((launch_dw<1, 2, 2, false>(xf, a0, d.B, c.st)));
-        DwArgs<2> a1{d.Tc, d.Fc, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_F1_EW], P[RTFS_P_F1_GW]}, {nullptr, nullptr}, {ge1, gg1}, {c.stat(RTFS_ST_F1E), c.stat(RTFS_ST_F1G)}, nullptr};
-        CK((launch_dw<1, 2, 2, false>(xf, a1, d.B, c.st)));
-    }
-    {
-        XfGln<0> xf{d1_pre, d.Tc, d.Fc, c.gln(RTFS_ST_D1, RTFS_P_D1_GAMMA, RTFS_P_D1_BETA, ncomp), nullptr};
-        DwArgs<1> a{d.Tc, d.Fc, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_F1_LW]}, {nullptr}, {le1}, {c.stat(RTFS_ST_F1L)}, nullptr};
-        STAGE(RTFS_SG_TFAR_GLOBAL);
-        CK((launch_dw<1, 4, 1, false>(xf, a, d.B, c.st)));
-    }
-    {
-        XfGln<0> xf{d0_pre, d.T, d.F, c.gln(RTFS_ST_D0, RTFS_P_D0_GAMMA, RTFS_P_D0_BETA, nfull), nullptr};
-        DwArgs<1> a{d.T, d.F, d.T, d.F, tseg_full, {P[RTFS_P_F0_LW]}, {nullptr}, {le0}, {c.stat(RTFS_ST_F0L)}, nullptr};
-        STAGE(RTFS_SG_TFAR_LE0);
-        CK((launch_dw<1, 4, 1, false>(xf, a, d.B, c.st)));
-    }
-    {
-        // f1 = TFAR_fus1(d1, g) formed on the fly -> the two global convs of concat_layers.0
-        XfTfar xf{le1, gg1, ge1, d.Tc, d.Fc, d.Tc, d.Fc,
-                  c.gln(RTFS_ST_F1L, RTFS_P_F1_LG, RTFS_P_F1_LB, ncomp), c.gln(RTFS_ST_F1G, RTFS_P_F1_GG, RTFS_P_F1_GB, ncomp),
-                  c.gln(RTFS_ST_F1E, RTFS_P_F1_EG, RTFS_P_F1_EB, ncomp)};
-        DwArgs<2> a{d.Tc, d.Fc, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_C0_EW], P[RTFS_P_C0_GW]}, {nullptr, nullptr}, {gec, ggc}, {c.stat(RTFS_ST_C0E), c.stat(RTFS_ST_C0G)}, nullptr};
-        STAGE(RTFS_SG_TFAR_CAT_GLOBAL);
-        CK((launch_dw<1, 2, 2, false>(xf, a, d.B, c.st)));
-    }
-    {
-        // f0 = TFAR_fus0(d0, g) formed on the fly -> local conv of concat_layers.0
-        XfTfar xf{le0, gg0, ge0, d.T, d.F, d.Tc, d.Fc,
-                  c.gln(RTFS_ST_F0L, RTFS_P_F0_LG, RTFS_P_F0_LB, nfull), c.gln(RTFS_ST_F0G, RTFS_P_F0_GG, RTFS_P_F0_GB, ncomp),
-                  c.gln(RTFS_ST_F0E, RTFS_P_F0_EG, RTFS_P_F0_EB, ncomp)};
-        DwArgs<1> a{d.T, d.F, d.T, d.F, tseg_full, {P[RTFS_P_C0_LW]}, {nullptr}, {lec}, {c.stat(RTFS_ST_C0L)}, nullptr};
-        STAGE(RTFS_SG_TFAR_CAT_LOCAL);
-        CK((launch_dw<1, 4, 1, false>(xf, a, d.B, c.st)));
+    if (roll) {
+        // S10-S12 TF-AR units                                                  tdanet.py:124-129, layers/fusion.py:54-69
+        {
+            // the four "global" convs (embedding + gate of fusion_layers.0 and .1) share their input g3
+            XrPlain xf{g3, d.Tc, d.Fc};
+            DrArgs<4> a{};
+            a.Ti = d.Tc; a.Fi = d.Fc;
+            a.w[0] = P[RTFS_P_F0_EW]; a.out[0] = ge0; a.sums[0] = c.stat(RTFS_ST_F0E);
+            a.w[1] = P[RTFS_P_F0_GW]; a.out[1] = gg0; a.sums[1] = c.stat(RTFS_ST_F0G);
+            a.w[2] = P[RTFS_P_F1_EW]; a.out[2] = ge1; a.sums[2] = c.stat(RTFS_ST_F1E);
+            a.w[3] = P[RTFS_P_F1_GW]; a.out[3] = gg1; a.sums[3] = c.stat(RTFS_ST_F1G);
+            STAGE(RTFS_SG_TFAR_GLOBAL);
+            CK((launch_dwroll<XrPlain, 4, false, 128>(xf, a, d.B, c.st)));
+        }
+        {
+            XrGln<0> xf{d1_pre, d.Tc, d.Fc, c.gln(RTFS_ST_D1, RTFS_P_D1_GAMMA, RTFS_P_D1_BETA, ncomp), nullptr};
+            DrArgs<1> a{};
+            a.Ti = d.Tc; a.Fi = d.Fc;
+            a.w[0] = P[RTFS_P_F1_LW]; a.out[0] = le1; a.sums[0] = c.stat(RTFS_ST_F1L);
+            STAGE(RTFS_SG_TFAR_GLOBAL);
+            CK((launch_dwroll<XrGln<0>, 1, false, 128>(xf, a, d.B, c.st)));
+        }
+        {
+            // f1 = TFAR_fus1(d1, g) formed on the fly -> the two global convs of concat_layers.0
+            XrTfar xf{le1, gg1, ge1, d.Tc, d.Fc, d.Tc, d.Fc,
+                      c.gln(RTFS_ST_F1L, RTFS_P_F1_LG, RTFS_P_F1_LB, ncomp), c.gln(RTFS_ST_F1G, RTFS_P_F1_GG, RTFS_P_F1_GB, ncomp),
+                      c.gln(RTFS_ST_F1E, RTFS_P_F1_EG, RTFS_P_F1_EB, ncomp)};
+            DrArgs<2> a{};
+            a.Ti = d.Tc; a.Fi = d.Fc;
+            a.w[0] = P[RTFS_P_C0_EW]; a.out[0] = gec; a.sums[0] = c.stat(RTFS_ST_C0E);
+            a.w[1] = P[RTFS_P_C0_GW]; a.out[1] = ggc; a.sums[1] = c.stat(RTFS_ST_C0G);
+            STAGE(RTFS_SG_TFAR_CAT_GLOBAL);
+            CK((launch_dwroll<XrTfar, 2, false, 128>(xf, a, d.B, c.st)));
+        }
+        {
+            // f0 = TFAR_fus0(d0, g) formed on the fly -> local conv of concat_layers.0
+            XrTfar xf{le0, gg0, ge0, d.T, d.F, d.Tc, d.Fc,
+                      c.gln(RTFS_ST_F0L, RTFS_P_F0_LG, RTFS_P_F0_LB, nfull), c.gln(RTFS_ST_F0G, RTFS_P_F0_GG, RTFS_P_F0_GB, ncomp),
+                      c.gln(RTFS_ST_F0E, RTFS_P_F0_EG, RTFS_P_F0_EB, ncomp)};
+            DrArgs<1> a{};
+            a.Ti = d.T; a.Fi = d.F;
+            a.w[0] = P[RTFS_P_C0_LW]; a.out[0] = lec; a.sums[0] = c.stat(RTFS_ST_C0L);
+            STAGE(RTFS_SG_TFAR_CAT_LOCAL);
+            CK((launch_dwroll<XrTfar, 1, false, 288>(xf, a, d.B, c.st)));
+        }
+    } else {
+        // S10-S12 TF-AR units                                                  tdanet.py:124-129, layers/fusion.py:54-69
+        {
+            XfPlain xf{g3, d.Tc, d.Fc};
+            STAGE(RTFS_SG_TFAR_GLOBAL);
+            DwArgs<2> a0{d.Tc, d.Fc, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_F0_EW], P[RTFS_P_F0_GW]}, {nullptr, nullptr}, {ge0, gg0}, {c.stat(RTFS_ST_F0E), c.stat(RTFS_ST_F0G)}, nullptr};
+            CK((launch_dw<1, 2, 2, false>(xf, a0, d.B, c.st)));
+            DwArgs<2> a1{d.Tc, d.Fc, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_F1_EW], P[RTFS_P_F1_GW]}, {nullptr, nullptr}, {ge1, gg1}, {c.stat(RTFS_ST_F1E), c.stat(RTFS_ST_F1G)}, nullptr};
+            CK((launch_dw<1, 2, 2, false>(xf, a1, d.B, c.st)));
+        }
+        {
+            XfGln<0> xf{d1_pre, d.Tc, d.Fc, c.gln(RTFS_ST_D1, RTFS_P_D1_GAMMA, RTFS_P_D1_BETA, ncomp), nullptr};
+            DwArgs<1> a{d.Tc, d.Fc, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_F1_LW]}, {nullptr}, {le1}, {c.stat(RTFS_ST_F1L)}, nullptr};
+            STAGE(RTFS_SG_TFAR_GLOBAL);
+            CK((launch_dw<1, 4, 1, false>(xf, a, d.B, c.st)));
+        }
+        {
+            XfGln<0> xf{d0_pre, d.T, d.F, c.gln(RTFS_ST_D0, RTFS_P_D0_GAMMA, RTFS_P_D0_BETA, nfull), nullptr};
+            DwArgs<1> a{d.T, d.F, d.T, d.F, tseg_full, {P[RTFS_P_F0_LW]}, {nullptr}, {le0}, {c.stat(RTFS_ST_F0L)}, nullptr};
+            STAGE(RTFS_SG_TFAR_LE0);
+            CK((launch_dw<1, 4, 1, false>(xf, a, d.B, c.st)));
+        }
+        {
+            // f1 = TFAR_fus1(d1, g) formed on the fly -> the two global convs of concat_layers.0
+            XfTfar xf{le1, gg1, ge1, d.Tc, d.Fc, d.Tc, d.Fc,
+                      c.gln(RTFS_ST_F1L, RTFS_P_F1_LG, RTFS_P_F1_LB, ncomp), c.gln(RTFS_ST_F1G, RTFS_P_F1_GG, RTFS_P_F1_GB, ncomp),
+                      c.gln(RTFS_ST_F1E, RTFS_P_F1_EG, RTFS_P_F1_EB, ncomp)};
+            DwArgs<2> a{d.Tc, d.Fc, d.Tc, d.Fc, tseg_comp, {P[RTFS_P_C0_EW], P[RTFS_P_C0_GW]}, {nullptr, nullptr}, {gec, ggc}, {c.stat(RTFS_ST_C0E), c.stat(RTFS_ST_C0G)}, nullptr};
+            STAGE(RTFS_SG_TFAR_CAT_GLOBAL);
+            CK((launch_dw<1, 2, 2, false>(xf, a, d.B, c.st)));
+        }
+        {
+            // f0 = TFAR_fus0(d0, g) formed on the fly -> local conv of concat_layers.0
+            XfTfar xf{le0, gg0, ge0, d.T, d.F, d.Tc, d.Fc,
+                      c.gln(RTFS_ST_F0L, RTFS_P_F0_LG, RTFS_P_F0_LB, nfull), c.gln(RTFS_ST_F0G, RTFS_P_F0_GG, RTFS_P_F0_GB, ncomp),
+                      c.gln(RTFS_ST_F0E, RTFS_P_F0_EG, RTFS_P_F0_EB, ncomp)};
+            DwArgs<1> a{d.T, d.F, d.T, d.F, tseg_full, {P[RTFS_P_C0_LW]}, {nullptr}, {lec}, {c.stat(RTFS_ST_C0L)}, nullptr};
+            STAGE(RTFS_SG_TFAR_CAT_LOCAL);
+            CK((launch_dw<1, 4, 1, false>(xf, a, d.B, c.st)));
+        }
     }
     // S13 e = TFAR_cat0(f0,f1) + d0 on the fly -> residual_conv + gateway(x) [+ addend]     tdanet.py:127-131
     {

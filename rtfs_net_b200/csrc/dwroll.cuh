@@ -1,0 +1,368 @@
+// Rolling-row depthwise 4x4 convolutions of the RTFS block on channels-last (B,T,F,64) tensors
+// (reference: ConvNormAct with groups=C, layers/conv_layers.py:65-129; the down-samplers tdanet.py:61-76
+// and the three TF-AR units layers/fusion.py:25-52).  Second generation of dwconv.cuh:
+//
+//   * one CTA owns (utterance b, a 16-channel group, a segment of output rows) and marches down T;
+//   * every input row is fetched from HBM exactly once per CTA with 16-byte cp.async into a ring of
+//     DR_NR shared-memory row slots (DR_NR-1 rows = 40-80 KB in flight per CTA, no registers tied up),
+//     the ring slot of row r is recycled for row r+DR_NR one barrier later;
+//   * thread = (channel pair, strip of 4 output columns): a 4-row x 7-column register window rolls down T,
+//     so each shared-memory row is read once, when it becomes the newest row of the window;
+//   * the input is produced on the fly by a functor (gLN-apply / PReLU / TF-AR combine with nearest
+//     up-sampling), so normalised tensors are never materialised; zero padding is applied after it;
+//   * NW convolutions can share one input (the four "global" convs of the TF-AR units); DUAL adds the
+//     stride-2 down-sampler + the 3x3/2 adaptive average pool on the same window (tdanet.py:69-76,117);
+//   * epilogue: per-sample (sum, sumsq) of every output for the following gLN, one fp64 atomic pair per CTA.
+//
+//   out[t][f][c] = bias[c] + sum_{i,j<4} w[c][i][j] * X[S*t-1+i][S*f-1+j][c]   (zero outside), S = 1 (or 2 for DUAL's second output)
+#pragma once
+#include "common.cuh"
+
+namespace rtfs {
+
+constexpr int DR_CG = 16;  // channels per CTA (one 64-byte piece of every position)
+constexpr int DR_NR = 6;   // ring slots
+
+// position -> slot index; swaps neighbours in every other group of 4 so that the two strips a
+// half-warp covers hit different bank halves (positions are 64 bytes = 16 banks wide)
+DEVINL int dr_phys(int f) { return f ^ ((f >> 2) & 1); }
+
+DEVINL int nearest_src32(int dst, int n_in, int n_out) {  // small sizes: 32-bit arithmetic is exact
+    const int s = (dst * n_in) / n_out;
+    return s < n_in - 1 ? s : n_in - 1;
+}
+
+DEVINL void cp_async16_always(void* smem, const void* gmem) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+DEVINL void cp_async_wait_dyn(int n) {  // n in [0, DR_NR-2]
+    switch (n) {
+        case 0: cp_async_wait<0>(); break;
+        case 1: cp_async_wait<1>(); break;
+        case 2: cp_async_wait<2>(); break;
+        case 3: cp_async_wait<3>(); break;
+        default: cp_async_wait<4>(); break;
+    }
+}
+
+// copy the 16-channel piece of one (B,T,F,64) row into a slot: position f -> slot + dr_phys(f)*16
+DEVINL void dr_issue_row(float* slot, const float* row_base /* + cg*16 applied */, int Fi, int tid, int nthreads) {
+    for (int i = tid; i < Fi * 4; i += nthreads) {
+        const int pos = i >> 2, c = i & 3;
+        cp_async16_always(slot + dr_phys(pos) * 16 + c * 4, row_base + (long long)pos * 64 + c * 4);
+    }
+}
+
+// ---------------------------------------------------------------- input functors
+// contract: slot_floats() ; init(b, cg, pair, f0) ; issue(r, slot, tid, nthreads) for a valid input row r ;
+//           fetch(slot, q) -> transformed channel pair at window column q (f = f0-1+q, known to be in range)
+struct XrPlain {
+    const float* x;  // [B][Ti][Fi][64]
+    int Ti, Fi;
+    const float* base_;
+    int f0_, pair_;
+    __host__ __device__ __forceinline__ int slot_floats() const { return (Fi + 2) * 16; }
+    DEVINL void init(int b, int cg, int pair, int f0) {
+        base_ = x + (long long)b * Ti * Fi * 64 + cg * 16;
+        f0_ = f0;
+        pair_ = pair;
+    }
+    DEVINL void issue(int r, float* slot, int tid, int nthreads) const { dr_issue_row(slot, base_ + (long long)r * Fi * 64, Fi, tid, nthreads); }
+    DEVINL float2 fetch(const float* slot, int q) const {
+        return *reinterpret_cast<const float2*>(slot + dr_phys(f0_ - 1 + q) * 16 + 2 * pair_);
+    }
+};
+
+// X = act(gLN(x)) ; ACT 0 none / 2 PReLU(slope)
+template <int ACT>
+struct XrGln {
+    const float* x;
+    int Ti, Fi;
+    GlnRef gln;
+    const float* slope;
+    const float* base_;
+    int f0_, pair_;
+    float2 sc_, sh_;
+    float a_;
+    __host__ __device__ __forceinline__ int slot_floats() const { return (Fi + 2) * 16; }
+    DEVINL void init(int b, int cg, int pair, int f0) {
+        base_ = x + (long long)b * Ti * Fi * 64 + cg * 16;
+        f0_ = f0;
+        pair_ = pair;
+        const int c = cg * 16 + 2 * pair;
+        float mean, rstd;
+        gln_mean_rstd(gln.sums, b, gln.inv_n, mean, rstd);
+        const float2 g = ldg2(gln.gamma + c), be = ldg2(gln.beta + c);
+        sc_ = make_float2(rstd * g.x, rstd * g.y);
+        sh_ = make_float2(be.x - mean * sc_.x, be.y - mean * sc_.y);
+        a_ = (ACT == 2) ? __ldg(slope) : 0.f;
+    }
+    DEVINL void issue(int r, float* slot, int tid, int nthreads) const { dr_issue_row(slot, base_ + (long long)r * Fi * 64, Fi, tid, nthreads); }
+    DEVINL float2 fetch(const float* slot, int q) const {
+        const float2 v = *reinterpret_cast<const float2*>(slot + dr_phys(f0_ - 1 + q) * 16 + 2 * pair_);
+        float2 y = make_float2(fmaf(v.x, sc_.x, sh_.x), fmaf(v.y, sc_.y, sh_.y));
+        if (ACT == 2) {
+            y.x = prelu(y.x, a_);
+            y.y = prelu(y.y, a_);
+        }
+        return y;
+    }
+};
+
+// X = TF-AR output (layers/fusion.py:54-69) formed on the fly:
+//   gLN_l(l)[t][f] * sigmoid(gLN_g(g))[near(t)][near(f)] + gLN_e(e)[near(t)][near(f)]
+// l at (Ti,Fi); g, e at (Tg,Fg) (nearest up-sampling; identity when the sizes are equal).
+struct XrTfar {
+    const float* l;
+    const float* g;
+    const float* e;
+    int Ti, Fi, Tg, Fg;
+    GlnRef nl, ng, ne;
+    const float *bl_, *bg_, *be_;
+    int f0_, pair_, lfl_, gfl_;
+    int gofs_[7];  // slot offset of the up-sampled column of each window column
+    float2 scl_, shl_, scg_, shg_, sce_, she_;
+    __host__ __device__ __forceinline__ int slot_floats() const { return (Fi + 2) * 16 + 2 * (Fg + 2) * 16; }
+    DEVINL void mk(const GlnRef& r, int b, int c, float2& sc, float2& sh) {
+        float mean, rstd;
+        gln_mean_rstd(r.sums, b, r.inv_n, mean, rstd);
+        const float2 gm = ldg2(r.gamma + c), be = ldg2(r.beta + c);
+        sc = make_float2(rstd * gm.x, rstd * gm.y);
+        sh = make_float2(be.x - mean * sc.x, be.y - mean * sc.y);
+    }
+    DEVINL void init(int b, int cg, int pair, int f0) {
+        bl_ = l + (long long)b * Ti * Fi * 64 + cg * 16;
+        bg_ = g + (long long)b * Tg * Fg * 64 + cg * 16;
+        be_ = e + (long long)b * Tg * Fg * 64 + cg * 16;
+        f0_ = f0;
+        pair_ = pair;
+        lfl_ = (Fi + 2) * 16;
+        gfl_ = (Fg + 2) * 16;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            int f = f0 - 1 + q;
+            f = f < 0 ? 0 : (f > Fi - 1 ? Fi - 1 : f);
+            gofs_[q] = lfl_ + dr_phys(nearest_src32(f, Fg, Fi)) * 16 + 2 * pair;
+        }
+        const int c = cg * 16 + 2 * pair;
+        mk(nl, b, c, scl_, shl_);
+        mk(ng, b, c, scg_, shg_);
+        mk(ne, b, c, sce_, she_);
+    }
+    DEVINL void issue(int r, float* slot, int tid, int nthreads) const {
+        dr_issue_row(slot, bl_ + (long long)r * Fi * 64, Fi, tid, nthreads);
+        const int rg = nearest_src32(r, Tg, Ti);
+        dr_issue_row(slot + lfl_, bg_ + (long long)rg * Fg * 64, Fg, tid, nthreads);
+        dr_issue_row(slot + lfl_ + gfl_, be_ + (long long)rg * Fg * 64, Fg, tid, nthreads);
+    }
+    DEVINL float2 fetch(const float* slot, int q) const {
+        const int f = f0_ - 1 + q;
+        const float2 vl = *reinterpret_cast<const float2*>(slot + dr_phys(f) * 16 + 2 * pair_);
+        const float2 vg = *reinterpret_cast<const float2*>(slot + gofs_[q]);
+        const float2 ve = *reinterpret_cast<const float2*>(slot + gofs_[q] + gfl_);
+        float2 y;
+        y.x = fmaf(vl.x, scl_.x, shl_.x) * sigmoidf_fast(fmaf(vg.x, scg_.x, shg_.x)) + fmaf(ve.x, sce_.x, she_.x);
+        y.y = fmaf(vl.y, scl_.y, shl_.y) * sigmoidf_fast(fmaf(vg.y, scg_.y, shg_.y)) + fmaf(ve.y, sce_.y, she_.y);
+        return y;
+    }
+};
+
+template <int NW>
+struct DrArgs {
+    int Ti, Fi;             // input = stride-1 output size
+    int rows_per_seg;       // output rows per CTA
+    const float* w[NW];     // [16][64] tap-major
+    const float* bias[NW];  // [64] or null
+    float* out[NW];         // [B][Ti][Fi][64]
+    double* sums[NW];       // [B][2] or null
+    // DUAL: stride-2 conv (pad 1) + adaptive average pool onto (To2, Fo2)
+    const float* w2;
+    const float* bias2;
+    float* out2;
+    double* sums2;
+    float* pool;
+    int To2, Fo2;
+};
+
+// NT threads = 8 channel pairs x NT/8 strips of 4 columns  (NT/8 >= ceil(Fi/4))
+template <class XF, int NW, bool DUAL, int NT>
+__global__ void __launch_bounds__(NT, (NT > 256 ? 2 : 4)) dwroll_kernel(XF xf, DrArgs<NW> a) {
+    constexpr int NCONV = NW + (DUAL ? 1 : 0);
+    extern __shared__ __align__(16) float dr_smem[];
+    __shared__ float wsm[NCONV][16][DR_CG];  // filter taps of this channel group
+    __shared__ float bsm[NCONV][DR_CG];
+    __shared__ float scratch[2 * (NT / 32)];
+
+    const int tid = threadIdx.x, pair = tid & 7, strip = tid >> 3;
+    const int cg = blockIdx.x & 3, seg = blockIdx.x >> 2, b = blockIdx.y;
+    const int Ti = a.Ti, Fi = a.Fi;
+    const int f0 = 4 * strip;
+    const bool active = f0 < Fi;
+    const int t0 = seg * a.rows_per_seg;
+    const int t1 = min(t0 + a.rows_per_seg, Ti);
+    const int slot_fl = xf.slot_floats();
+
+    for (int i = tid; i < NCONV * 16 * DR_CG; i += NT) {
+        const int w = i / (16 * DR_CG), rem = i - w * 16 * DR_CG, tap = rem / DR_CG, c = rem - tap * DR_CG;
+        const float* wp = (DUAL && w == NW) ? a.w2 : a.w[w < NW ? w : 0];
+        wsm[w][tap][c] = __ldg(wp + tap * 64 + cg * DR_CG + c);
+    }
+    for (int i = tid; i < NCONV * DR_CG; i += NT) {
+        const int w = i / DR_CG, c = i - w * DR_CG;
+        const float* bp = (DUAL && w == NW) ? a.bias2 : a.bias[w < NW ? w : 0];
+        bsm[w][c] = bp ? __ldg(bp + cg * DR_CG + c) : 0.f;
+    }
+    xf.init(b, cg, pair, active ? f0 : 0);
+
+    // input rows r = t0-1 .. t1+1 ; row r lives in slot (r - (t0-1)) % DR_NR
+    const int r_first = t0 - 1, r_last = t1 + 1;
+    auto issue = [&](int r) {
+        if (r >= 0 && r < Ti && r <= r_last) xf.issue(r, dr_smem + ((r - r_first) % DR_NR) * slot_fl, tid, NT);
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < DR_NR - 1; ++i) issue(r_first + i);
+
+    float2 win[4][7];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 7; ++q) win[i][q] = make_float2(0.f, 0.f);
+    float st_s[NCONV], st_q[NCONV];
+#pragma unroll
+    for (int w = 0; w < NCONV; ++w) st_s[w] = st_q[w] = 0.f;
+
+    const int wT = 2 + (Ti & 1), wF = 2 + (Fi & 1);
+    const float pool_scale = 1.f / (float)(wT * wF);
+    const int c0 = cg * DR_CG + 2 * pair;
+
+    for (int r = r_first; r <= r_last; ++r) {
+        cp_async_wait<DR_NR - 2>();  // this thread's pieces of row r have landed
+        __syncthreads();             // everyone's have; everyone is done reading row r-1's slot
+        issue(r + DR_NR - 1);        // -> into the slot of row r-1
+        // roll the window and bring in row r
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            win[0][q] = win[1][q];
+            win[1][q] = win[2][q];
+            win[2][q] = win[3][q];
+        }
+        const bool rvalid = r >= 0 && r < Ti;
+        const float* slot = dr_smem + ((r - r_first) % DR_NR) * slot_fl;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            const int f = f0 - 1 + q;
+            win[3][q] = (active && rvalid && f >= 0 && f < Fi) ? xf.fetch(slot, q) : make_float2(0.f, 0.f);
+        }
+        const int t = r - 2;  // output row whose window (rows t-1..t+2) is now complete
+        if (t < t0 || !active) continue;
+        // ---- stride-1 outputs
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            float2 acc[4];
+            const float2 bs = *reinterpret_cast<const float2*>(&bsm[w][2 * pair]);
+#pragma unroll
+            for (int o = 0; o < 4; ++o) acc[o] = bs;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 wv = *reinterpret_cast<const float2*>(&wsm[w][i * 4 + j][2 * pair]);
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        acc[o].x = fmaf(wv.x, win[i][o + j].x, acc[o].x);
+                        acc[o].y = fmaf(wv.y, win[i][o + j].y, acc[o].y);
+                    }
+                }
+            float* orow = a.out[w] + (((long long)b * Ti + t) * Fi + f0) * 64 + c0;
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                if (f0 + o < Fi) {
+                    *reinterpret_cast<float2*>(orow + o * 64) = acc[o];
+                    st_s[w] += acc[o].x + acc[o].y;
+                    st_q[w] += acc[o].x * acc[o].x + acc[o].y * acc[o].y;
+                }
+        }
+        // ---- stride-2 output row t/2 and the adaptive average pool
+        if (DUAL && (t & 1) == 0 && (t >> 1) < a.To2) {
+            const int to = t >> 1;
+            const float2 bs = *reinterpret_cast<const float2*>(&bsm[NW][2 * pair]);
+            float2 acc[2] = {bs, bs};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 wv = *reinterpret_cast<const float2*>(&wsm[NW][i * 4 + j][2 * pair]);
+#pragma unroll
+                    for (int o = 0; o < 2; ++o) {
+                        acc[o].x = fmaf(wv.x, win[i][2 * o + j].x, acc[o].x);
+                        acc[o].y = fmaf(wv.y, win[i][2 * o + j].y, acc[o].y);
+                    }
+                }
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+                const int fo = (f0 >> 1) + o;
+                if (fo < a.Fo2) {
+                    const long long off = (((long long)b * a.To2 + to) * a.Fo2 + fo) * 64 + c0;
+                    *reinterpret_cast<float2*>(a.out2 + off) = acc[o];
+                    st_s[NW] += acc[o].x + acc[o].y;
+                    st_q[NW] += acc[o].x * acc[o].x + acc[o].y * acc[o].y;
+                    float2 p = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int i = 1; i < 4; ++i)
+#pragma unroll
+                        for (int j = 1; j < 4; ++j)
+                            if (i <= wT && j <= wF) {
+                                p.x += win[i][2 * o + j].x;
+                                p.y += win[i][2 * o + j].y;
+                            }
+                    *reinterpret_cast<float2*>(a.pool + off) = make_float2(p.x * pool_scale, p.y * pool_scale);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int w = 0; w < NCONV; ++w) {
+        double* dst = (DUAL && w == NW) ? a.sums2 : a.sums[w < NW ? w : 0];
+        block_stats_atomic(st_s[w], st_q[w], dst ? dst + 2 * b : nullptr, scratch);
+    }
+}
+
+// rows per CTA: as few segments as keep the 3-row halo re-read small while filling 148 SMs evenly
+inline int dr_rows_per_seg(int T, int B, int ctas_per_sm) {
+    const int slots = 148 * ctas_per_sm;
+    int best = T;
+    double best_eff = 0.0;
+    for (int nseg = 1; nseg <= 24 && nseg <= T; ++nseg) {
+        const int rows = (T + nseg - 1) / nseg;
+        const int nseg_eff = (T + rows - 1) / rows;
+        const long long ctas = (long long)B * 4 * nseg_eff;
+        const long long waves = (ctas + slots - 1) / slots;
+        const double eff = ((double)ctas / (double)(waves * slots)) * ((double)rows / (double)(rows + 3 + DR_NR - 1));
+        if (eff > best_eff) {
+            best_eff = eff;
+            best = rows;
+        }
+    }
+    return best;
+}
+
+template <class XF, int NW, bool DUAL, int NT>
+inline cudaError_t launch_dwroll(const XF& xf, DrArgs<NW> a, int B, cudaStream_t st) {
+    auto kern = dwroll_kernel<XF, NW, DUAL, NT>;
+    const int smem = DR_NR * xf.slot_floats() * 4;
+    static int configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    a.rows_per_seg = dr_rows_per_seg(a.Ti, B, 2);
+    const int nseg = (a.Ti + a.rows_per_seg - 1) / a.rows_per_seg;
+    kern<<<dim3(4 * nseg, B), NT, smem, st>>>(xf, a);
+    return cudaGetLastError();
+}
+
+}  // namespace rtfs
