@@ -31,6 +31,10 @@ bool use_roll() {  // RTFS_LEGACY_DW=1: first-generation depthwise kernels (dwco
     static const bool v = !env_flag("RTFS_LEGACY_DW");
     return v;
 }
+bool use_unfold() {  // RTFS_NO_UNFOLD=1: overlapping-view GEMMs through the generic im2col-style loader
+    static const bool v = !env_flag("RTFS_NO_UNFOLD");
+    return v;
+}
 bool use_tc() {
     static const bool v = !env_flag("RTFS_LEGACY_GEMM");
     return v;
@@ -262,7 +266,8 @@ int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_f
             STAGE(RTFS_SG_DPRNN_GEMM0);
             if (use_tc()) {
                 StoreEpi4 ep{U, 256, nullptr};
-                CK((launch_gemm_tc<256, 512, 3, 1>(al, c.P[basei + 0], ep, M, c.st)));
+                if (use_unfold()) CK((launch_gemm_tc_unfold<256, 3, 1>(n, c.P[basei + 0], ep, M, c.st)));
+                else CK((launch_gemm_tc<256, 512, 3, 1>(al, c.P[basei + 0], ep, M, c.st)));
             } else {
                 StoreEpi ep{U, 256, nullptr};
                 CK((launch_gemm<128, 512, false>(al, c.P[base + 2], ep, M, 256, c.st)));
@@ -301,7 +306,8 @@ int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_f
         STAGE(RTFS_SG_DPRNN_CONVT);
         if (use_tc()) {
             ConvTEpi4 ep{g_out, resid, c.P[base + 15], S, n_other, which, d.Tc, d.Fc};
-            CK((launch_gemm_tc<64, 512, 4, 2>(al, c.P[basei + 4], ep, nseq * (S + 7), c.st)));
+            if (use_unfold()) CK((launch_gemm_tc_unfold<64, 4, 2>(hpad, c.P[basei + 4], ep, nseq * (S + 7), c.st)));
+            else CK((launch_gemm_tc<64, 512, 4, 2>(al, c.P[basei + 4], ep, nseq * (S + 7), c.st)));
         } else {
             ConvTEpi ep{g_out, resid, c.P[base + 15], S, n_other, which, d.Tc, d.Fc};
             CK((launch_gemm<64, 512, false>(al, c.P[base + 14], ep, nseq * (S + 7), 64, c.st)));

@@ -368,6 +368,142 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) gemm_tc_kernel(AL al, const 
     if (warp == 0) tmem_dealloc<TCOLS>(tmem);
 }
 
+// ---------------------------------------------------------------------------------- overlapping-view variant
+// C[M x BN] = A_view[M x 8*64] * W^T where A_view[r][tap*64+c] = X[(r+tap)*64 + c] (nn.Unfold(8) o Linear of
+// the dual-path RNN, and ConvTranspose1d(k=8) over the zero-padded h).  The (128+7) x 64 slab of X is staged
+// ONCE in the K-major no-swizzle layout; tap t is then just the same slab with the descriptor start address
+// advanced by t rows (t*16 bytes) -- no im2col copy, 8x less shared-memory fill than the generic kernel.
+constexpr int TCU_ROWS = TC_BM + 8;                 // 136 rows staged (135 needed)
+constexpr int TCU_LBO = TCU_ROWS * 16 + 16;         // 2192
+constexpr int TCU_A_BYTES = 16 * TCU_LBO;           // 16 K-pieces of 4 channels = 35072
+
+template <int BN, int NS>
+__host__ __device__ constexpr int tcu_smem_bytes() {
+    return (TCU_A_BYTES + NS * BN * 128 > TC_STG_BYTES ? TCU_A_BYTES + NS * BN * 128 : TC_STG_BYTES) + 256 + 128;
+}
+
+template <int BN, int NS, int MINB, class EP>
+__global__ void __launch_bounds__(TC_THREADS, MINB) gemm_tc_unfold_kernel(const float* __restrict__ X, const float* __restrict__ Wimg, EP ep, int M) {
+    constexpr int NK = 16;  // 8 taps x 2 halves of 32 channels
+    constexpr int WBYTES = BN * 128;
+    constexpr int TCOLS = tc_tmem_cols<BN>();
+    constexpr int AREA = TCU_A_BYTES + NS * WBYTES > TC_STG_BYTES ? TCU_A_BYTES + NS * WBYTES : TC_STG_BYTES;
+    static_assert(NS >= 2, "ring");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* a_slab = smem_raw;
+    unsigned char* w_stage = smem_raw + TCU_A_BYTES;
+    uint64_t* full_w = reinterpret_cast<uint64_t*>(smem_raw + AREA);
+    uint64_t* mma_done = full_w + NS;
+    uint64_t* acc_ready = mma_done + NS;  // single-phase: only thread 0 tracks the ring phases
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
+    float* scratch = reinterpret_cast<float*>(tmem_slot + 4);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row0 = blockIdx.x * TC_BM;
+    if (warp == 0) tmem_alloc<TCOLS>(tmem_slot);
+    if (tid == 32) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(full_w + s, 1);
+            mbar_init(mma_done + s, 1);
+        }
+        mbar_init(acc_ready, 1);
+        fence_mbar_init();
+    }
+    ep.init(row0, M);
+    // stage rows row0 .. row0+135 (rows past M+7 are never multiplied into a stored output: zero them)
+    for (int i = tid; i < TCU_ROWS * 16; i += TC_THREADS) {
+        const int r = i >> 4, kq = i & 15;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < M + 7) v = ldg4(X + (long long)(row0 + r) * 64 + kq * 4);
+        v.x = tf32r(v.x);
+        v.y = tf32r(v.y);
+        v.z = tf32r(v.z);
+        v.w = tf32r(v.w);
+        *reinterpret_cast<float4*>(a_slab + kq * TCU_LBO + r * 16) = v;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    constexpr uint32_t IDESC = umma_idesc_tf32(TC_BM, BN);
+    if (tid == 0) {
+        auto issue_w = [&](int c) {
+            const int s = c % NS;
+            mbar_expect_tx(full_w + s, WBYTES);
+            bulk_g2s(w_stage + (size_t)s * WBYTES, Wimg + (size_t)c * (BN * TC_KC), WBYTES, full_w + s);
+        };
+#pragma unroll
+        for (int c = 0; c < NS; ++c) issue_w(c);
+        const uint32_t a_base = smem_u32(a_slab);
+#pragma unroll 1
+        for (int kc = 0; kc < NK; ++kc) {
+            const int s = kc % NS;
+            mbar_wait(full_w + s, (kc / NS) & 1);
+            tc_fence_after();
+            const uint32_t w_base = smem_u32(w_stage + (size_t)s * WBYTES);
+            const int tap = kc >> 1, half = kc & 1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint64_t da = umma_desc(a_base + (half * 8 + 2 * q) * TCU_LBO + tap * 16, TCU_LBO, 128);
+                const uint64_t db = umma_desc(w_base + 2 * q * (BN * 16), BN * 16, 128);
+                umma_tf32(tmem, da, db, IDESC, (kc > 0 || q > 0) ? 1u : 0u);
+            }
+            umma_commit(mma_done + s);
+            if (kc + NS < NK) {  // refill this stage once its MMAs have drained
+                mbar_wait(mma_done + s, (kc / NS) & 1);
+                issue_w(kc + NS);
+            }
+        }
+        umma_commit(acc_ready);
+    }
+    mbar_wait(acc_ready, 0);
+    tc_fence_after();
+    {
+        const int q = warp & 3, hlf = warp >> 2;
+        float* stg = reinterpret_cast<float*>(smem_raw) + warp * (32 * TC_STG_LD);
+        const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll 1
+        for (int cb = 0; cb < BN / 64; ++cb) {
+            const int col0 = hlf * (BN / 2) + cb * 32;
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(stg + lane * TC_STG_LD + 4 * i) =
+                    make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            __syncwarp();
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const int r = p * 4 + rsub;
+                const float4 x = *reinterpret_cast<const float4*>(stg + r * TC_STG_LD + c4);
+                const int row = row0 + q * 32 + r;
+                if (row < M) ep.store4(row, col0 + c4, x);
+            }
+            __syncwarp();
+        }
+    }
+    ep.finish(scratch);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<TCOLS>(tmem);
+}
+
+template <int BN, int NS, int MINB, class EP>
+inline cudaError_t launch_gemm_tc_unfold(const float* X, const float* Wimg, const EP& ep, int M, cudaStream_t st) {
+    auto kern = gemm_tc_unfold_kernel<BN, NS, MINB, EP>;
+    const int smem = tcu_smem_bytes<BN, NS>();
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<(M + TC_BM - 1) / TC_BM, TC_THREADS, smem, st>>>(X, Wimg, ep, M);
+    return cudaGetLastError();
+}
+
 template <int BN, int KTOT, int NS, int MINB, class AL, class EP>
 inline cudaError_t launch_gemm_tc(const AL& al, const float* Wimg, const EP& ep, int M, cudaStream_t st) {
     auto kern = gemm_tc_kernel<BN, KTOT, NS, MINB, AL, EP>;
