@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RTFS_ABI_VERSION 2
+#define RTFS_ABI_VERSION 3
 #define RTFS_F 129
 #define RTFS_FC 64
 
@@ -73,6 +73,9 @@ enum rtfs_param {
     RTFS_P_BN_WI, RTFS_P_PJ_WI, RTFS_P_RC_WI, RTFS_P_MK_WI,
     RTFS_P_RF_WI0, RTFS_P_RF_WI1, RTFS_P_RF_WI2, RTFS_P_RF_WI3, RTFS_P_RF_CTWI,
     RTFS_P_RT_WI0, RTFS_P_RT_WI1, RTFS_P_RT_WI2, RTFS_P_RT_WI3, RTFS_P_RT_CTWI,
+    /* fused dual-path RNN kernel: 52 slabs of 16 KB = SRU layer 0 (32), layers 1-3 (4 each), ConvTranspose1d (8),
+     * SRU slabs = [acc 2][K piece 4][TMEM lane 128][4] with lanes (candidate | reset) and (forget | highway) */
+    RTFS_P_RF_FUSED, RTFS_P_RT_FUSED,
     RTFS_P_COUNT
 };
 

@@ -9,6 +9,7 @@
 #include "attention.cuh"
 #include "caf.cuh"
 #include "dprnn.cuh"
+#include "dprnn_fused.cuh"
 #include "dwconv.cuh"
 #include "dwroll.cuh"
 #include "frontend.cuh"
@@ -29,6 +30,10 @@ bool env_flag(const char* name) {
 }
 bool use_roll() {  // RTFS_LEGACY_DW=1: first-generation depthwise kernels (dwconv.cuh)
     static const bool v = !env_flag("RTFS_LEGACY_DW");
+    return v;
+}
+bool use_fused_dprnn() {  // RTFS_UNFUSED_DPRNN=1: prep + GEMM + scan kernels instead of dprnn_fused.cuh
+    static const bool v = !env_flag("RTFS_UNFUSED_DPRNN");
     return v;
 }
 bool use_unfold() {  // RTFS_NO_UNFOLD=1: overlapping-view GEMMs through the generic im2col-style loader
@@ -230,6 +235,37 @@ int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_f
     const int nseq = d.B * n_other;
     const int L = S - 7;
     if (L < 1) return fail_msg("dual-path RNN needs at least 8 steps along the scanned axis");
+    if (use_tc() && use_fused_dprnn() && S <= DF_NP) {
+        DfArgs a;
+        memset(&a, 0, sizeof(a));
+        a.g_in = g_in;
+        a.d1_pre = c.buf(RTFS_WS_D1_PRE);
+        a.pool = c.buf(RTFS_WS_POOL);
+        a.gln = c.gln(RTFS_ST_D1, RTFS_P_D1_GAMMA, RTFS_P_D1_BETA, d.Pc * 64);
+        a.g_first = g_first;
+        a.ln_gamma = c.P[base + 0];
+        a.ln_beta = c.P[base + 1];
+        a.wimg = c.P[which == 0 ? RTFS_P_RF_FUSED : RTFS_P_RT_FUSED];
+        for (int l = 0; l < 4; ++l) {
+            a.wc[l] = c.P[base + 3 + 3 * l];
+            a.bias[l] = c.P[base + 4 + 3 * l];
+        }
+        a.ct_bias = c.P[base + 15];
+        a.g_out = g_out;
+        a.B = d.B;
+        a.Tc = d.Tc;
+        a.Fc = d.Fc;
+        a.time_path = which;
+        a.first = first ? 1 : 0;
+        a.S = S;
+        a.L = L;
+        a.nseq_total = nseq;
+        a.n_other = n_other;
+        a.nseq_tile = DF_NP / S < 4 ? DF_NP / S : 4;
+        STAGE(RTFS_SG_DPRNN_GEMM0);
+        CK(launch_dprnn_fused(a, c.st));
+        return 0;
+    }
     const int M = nseq * S;
     float* n = c.buf(RTFS_WS_N);
     float* U = c.buf(RTFS_WS_U);

@@ -1,0 +1,382 @@
+// Fused dual-path RNN (reference: DualPathRNN.forward, layers/rnn_layers.py:136-162; SRU recurrence per the
+// third-party `sru` package).  One kernel per path replaces prep + 5 GEMMs + 4 scans:
+//
+//   g (B,Tc,Fc,64) --LN over C--> n --unfold(8) . W0--> U0 --scan--> h0 --W1--> U1 --scan--> ... h3
+//     --ConvTranspose1d(64,64,8) + bias + residual--> g'
+//
+// A CTA owns a tile of up to 256 positions = NSEQ whole sequences packed back to back (frequency path:
+// 4 x 64 bins of one frame each; time path: 2 x 125 frames of one bin each).  Everything between the
+// load of g and the store of g' stays on chip:
+//   * the activation slab (n, then h0..h3 in place) lives in shared memory in the UMMA K-major no-swizzle
+//     layout with 7 guard rows either side; nn.Unfold(8) and the k=8 transposed conv are the SAME slab read
+//     through descriptors whose start address is advanced by `tap` rows (16 bytes each) -- no im2col;
+//   * the SRU GEMMs run transposed (features on the 128 TMEM lanes, positions on the columns):
+//         acc0 lanes 0-63 = candidate, 64-127 = reset pre-activation ; acc1 lanes 0-63 = forget pre-activation,
+//         64-127 = highway projection (layer 0)
+//     so the serial recurrence reads its own TMEM lane, 16 time steps per tcgen05.ld: warps (4s+0, 4s+1) run
+//     the c-recurrence of sequence s (forward / backward halves), warps (4s+2, 4s+3) then form h in parallel;
+//   * weights stream through a 5-stage ring of 16 KB slabs (one cp.async.bulk each, 52 slabs per tile,
+//     prefetched across phase boundaries by a dedicated producer thread);
+//   * the transposed conv runs with positions on the lanes, so its epilogue (bias + residual + store) is the
+//     coalesced transposed-through-shared-memory store of gemm_tc.cuh.
+#pragma once
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+namespace rtfs {
+
+constexpr int DF_NT = 512;
+constexpr int DF_NP = 256;                 // positions per tile
+constexpr int DF_ROWS = 7 + DF_NP + 7;     // slab rows (guard rows hold zeros)
+constexpr int DF_LBO = DF_ROWS * 16 + 16;  // 4336 bytes between 4-channel pieces
+constexpr int DF_HBUF = 16 * DF_LBO;       // 69376
+constexpr int DF_CS = DF_NP * 64 * 4;      // 65536: c_t of every (position, column)
+constexpr int DF_WCH = 16384;              // weight slab bytes
+constexpr int DF_NSTG = 5;
+constexpr int DF_NCHUNK = 32 + 3 * 4 + 8;  // layer 0 | layers 1-3 | transposed conv
+constexpr int DF_SMEM = DF_HBUF + DF_CS + DF_NSTG * DF_WCH + DF_NP * 4 + 256;
+
+struct DfArgs {
+    const float* g_in;    // (B,Tc,Fc,64) when first == 0
+    const float* d1_pre;  // first == 1: g = gLN(d1_pre) + pool (tdanet.py:117-118), also written to g_first
+    const float* pool;
+    GlnRef gln;
+    float* g_first;
+    const float* ln_gamma;  // [64]
+    const float* ln_beta;
+    const float* wimg;      // DF_NCHUNK slabs of 4096 floats (weights.py: dprnn_fused_image)
+    const float* wc[4];     // [128] = v_f | v_r per layer
+    const float* bias[4];   // [128] = b_f | b_r
+    const float* ct_bias;   // [64]
+    float* g_out;
+    int B, Tc, Fc;
+    int time_path;  // 0: sequences = (b,t), scanned axis f ; 1: sequences = (b,f), scanned axis t
+    int first;
+    int S, L;       // sequence length, SRU steps (S - 7)
+    int nseq_total, nseq_tile, n_other;
+};
+
+DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+DEVINL float sigmoid_from_neg_log2(float t) {  // t = -x*log2(e)  ->  1/(1+2^t)
+    return __fdividef(1.f, 1.f + exp2f(t));
+}
+
+__global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* hbuf = smem_raw;
+    float* cs = reinterpret_cast<float*>(smem_raw + DF_HBUF);
+    unsigned char* wring = smem_raw + DF_HBUF + DF_CS;
+    int* pos2off = reinterpret_cast<int*>(wring + DF_NSTG * DF_WCH);
+    uint64_t* full_w = reinterpret_cast<uint64_t*>(pos2off + DF_NP);
+    uint64_t* mma_done = full_w + DF_NSTG;
+    uint64_t* acc_ready = mma_done + DF_NSTG;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = warp & 3, sw = warp >> 2;
+    const int S = a.S, L = a.L;
+    const int seq0 = blockIdx.x * a.nseq_tile;
+
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    if (tid == 32) {
+#pragma unroll
+        for (int s = 0; s < DF_NSTG; ++s) {
+            mbar_init(full_w + s, 1);
+            mbar_init(mma_done + s, 1);
+        }
+        mbar_init(acc_ready, 1);
+        fence_mbar_init();
+    }
+    if (tid < DF_NP) {
+        const int p = tid;
+        const int s = p / S, l = p - s * S;
+        const int seqg = seq0 + s;
+        int off = -1;
+        if (s < a.nseq_tile && seqg < a.nseq_total) {
+            const int b = seqg / a.n_other, o = seqg - b * a.n_other;
+            const int t = a.time_path ? l : o, f = a.time_path ? o : l;
+            off = ((b * a.Tc + t) * a.Fc + f) * 64;
+        }
+        pos2off[p] = off;
+    }
+    // guard rows (7 before, 7 after) of every 4-channel piece
+    for (int i = tid; i < 14 * 16; i += DF_NT) {
+        const int kq = i / 14, rr = i - kq * 14;
+        const int row = rr < 7 ? rr : DF_NP + rr;
+        *reinterpret_cast<float4*>(hbuf + kq * DF_LBO + row * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    // ---- weight producer (thread 32): slab g -> ring slot g % 5
+    int wnext = 0;
+    auto produce_until = [&](int limit) {
+        if (limit > DF_NCHUNK) limit = DF_NCHUNK;
+        while (wnext < limit) {
+            const int slot = wnext % DF_NSTG;
+            if (wnext >= DF_NSTG) mbar_wait(mma_done + slot, ((wnext / DF_NSTG) - 1) & 1);
+            mbar_expect_tx(full_w + slot, DF_WCH);
+            bulk_g2s(wring + slot * DF_WCH, a.wimg + (size_t)wnext * (DF_WCH / 4), DF_WCH, full_w + slot);
+            ++wnext;
+        }
+    };
+    if (tid == 32) produce_until(DF_NSTG);
+
+    // ---- P0: g -> LayerNorm over C -> n (tf32) into the slab   (two batches of 4 rows per thread)
+    {
+        const int l16 = tid & 15, c = l16 * 4;
+        const float4 gm = ldg4(a.ln_gamma + c), be = ldg4(a.ln_beta + c);
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+            float4 v[4], pl[4];
+            int offs[4];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int p = (hh * 4 + it) * 32 + (tid >> 4);
+                offs[it] = pos2off[p];
+                v[it] = pl[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (offs[it] >= 0) {
+                    if (a.first) {
+                        v[it] = ldg4(a.d1_pre + offs[it] + c);
+                        pl[it] = ldg4(a.pool + offs[it] + c);
+                    } else {
+                        v[it] = ldg4(a.g_in + offs[it] + c);
+                    }
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int p = (hh * 4 + it) * 32 + (tid >> 4);
+                float4 x = v[it];
+                if (a.first && offs[it] >= 0) {
+                    const int b = offs[it] / (a.Tc * a.Fc * 64);
+                    float mean, rstd;
+                    gln_mean_rstd(a.gln.sums, b, a.gln.inv_n, mean, rstd);
+                    const float4 gg = ldg4(a.gln.gamma + c), gb = ldg4(a.gln.beta + c);
+                    x.x = (x.x - mean) * rstd * gg.x + gb.x + pl[it].x;
+                    x.y = (x.y - mean) * rstd * gg.y + gb.y + pl[it].y;
+                    x.z = (x.z - mean) * rstd * gg.z + gb.z + pl[it].z;
+                    x.w = (x.w - mean) * rstd * gg.w + gb.w + pl[it].w;
+                    *reinterpret_cast<float4*>(a.g_first + offs[it] + c) = x;
+                }
+                float s = x.x + x.y + x.z + x.w;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                const float mu = s * (1.f / 64.f);
+                const float dx = x.x - mu, dy = x.y - mu, dz = x.z - mu, dw = x.w - mu;
+                float qq = dx * dx + dy * dy + dz * dz + dw * dw;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+                const float rs = 1.f / sqrtf(qq * (1.f / 64.f) + RTFS_EPS);
+                float4 n;
+                n.x = tf32r(dx * rs * gm.x + be.x);
+                n.y = tf32r(dy * rs * gm.y + be.y);
+                n.z = tf32r(dz * rs * gm.z + be.z);
+                n.w = tf32r(dw * rs * gm.w + be.w);
+                if (offs[it] < 0) n = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(hbuf + l16 * DF_LBO + (7 + p) * 16) = n;
+            }
+        }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const uint32_t hbuf_u = smem_u32(hbuf);
+    const uint32_t ring_u = smem_u32(wring);
+    constexpr uint32_t IDESC_SRU = umma_idesc_tf32(128, 256);
+    constexpr uint32_t IDESC_CT = umma_idesc_tf32(128, 64);
+    const int p_lo = sw * S, p_hi = p_lo + L;
+    const bool seq_on = sw < a.nseq_tile;
+
+    int cbeg = 0;
+#pragma unroll 1
+    for (int ly = 0; ly < 4; ++ly) {
+        const int nch = ly == 0 ? 32 : 4;
+        // ---- GEMM: U^T[features][positions]
+        if (tid == 0) {
+            for (int gl = 0; gl < nch; ++gl) {
+                const int g = cbeg + gl, slot = g % DF_NSTG;
+                mbar_wait(full_w + slot, (g / DF_NSTG) & 1);
+                tc_fence_after();
+                const int tap = ly == 0 ? (gl >> 2) : 0;
+                const int cb = (ly == 0 ? (gl & 3) : gl) * 4;
+                const uint32_t st = ring_u + slot * DF_WCH;
+#pragma unroll
+                for (int k2 = 0; k2 < 2; ++k2) {
+                    const uint64_t db = umma_desc(hbuf_u + (cb + 2 * k2) * DF_LBO + (7 + tap) * 16, DF_LBO, 128);
+                    const uint32_t acc_on = (gl > 0 || k2 > 0) ? 1u : 0u;
+                    umma_tf32(tmem, umma_desc(st + 2 * k2 * 2048, 2048, 128), db, IDESC_SRU, acc_on);
+                    umma_tf32(tmem + 256, umma_desc(st + 8192 + 2 * k2 * 2048, 2048, 128), db, IDESC_SRU, acc_on);
+                }
+                umma_commit(mma_done + slot);
+            }
+            umma_commit(acc_ready);
+        } else if (tid == 32) {
+            produce_until(cbeg + nch + DF_NSTG);
+        }
+        cbeg += nch;
+        mbar_wait(acc_ready, ly & 1);
+        tc_fence_after();
+
+        // ---- c-recurrence: warps q = 0 (forward columns 0-31) and q = 1 (backward columns 32-63)
+        if (q < 2 && seq_on) {
+            const int j = q * 32 + lane;
+            const float nl2e = -1.4426950408889634f;
+            const float vf = __ldg(a.wc[ly] + j) * nl2e, bf = __ldg(a.bias[ly] + j);
+            const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+            float c = 0.f;
+            float* csj = cs + j;
+            if (q == 0) {
+                for (int m = p_lo >> 4; m <= (p_hi - 1) >> 4; ++m) {
+                    uint32_t ua[16], ub[16];
+                    tmem_ld16(tl + 16 * m, ua);
+                    tmem_ld16(tl + 256 + 16 * m, ub);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int p = 16 * m + i;
+                        if (p >= p_lo && p < p_hi) {
+                            const float u0 = __uint_as_float(ua[i]);
+                            const float f = sigmoid_from_neg_log2(fmaf(vf, c, (__uint_as_float(ub[i]) + bf) * nl2e));
+                            c = fmaf(f, c - u0, u0);
+                            csj[p * 64] = c;
+                        }
+                    }
+                }
+            } else {
+                for (int m = (p_hi - 1) >> 4; m >= p_lo >> 4; --m) {
+                    uint32_t ua[16], ub[16];
+                    tmem_ld16(tl + 16 * m, ua);
+                    tmem_ld16(tl + 256 + 16 * m, ub);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 15; i >= 0; --i) {
+                        const int p = 16 * m + i;
+                        if (p >= p_lo && p < p_hi) {
+                            const float u0 = __uint_as_float(ua[i]);
+                            const float f = sigmoid_from_neg_log2(fmaf(vf, c, (__uint_as_float(ub[i]) + bf) * nl2e));
+                            c = fmaf(f, c - u0, u0);
+                            csj[p * 64] = c;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- h: warps q = 2 (columns 0-31) and q = 3 (columns 32-63), every step independent
+        if (q >= 2 && seq_on) {
+            const int j = (q - 2) * 32 + lane;
+            const bool rev = q == 3;
+            const float nl2e = -1.4426950408889634f;
+            const float vr = __ldg(a.wc[ly] + 64 + j) * nl2e, br = __ldg(a.bias[ly] + 64 + j);
+            const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+            unsigned char* hb = hbuf + (j >> 2) * DF_LBO + 7 * 16 + (j & 3) * 4;
+            const float* csj = cs + j;
+            const int p_end = ly == 3 ? p_lo + S : p_hi;  // the last layer also zeroes the 7 tail rows (conv-transpose padding)
+            for (int m = p_lo >> 4; m <= (p_end - 1) >> 4; ++m) {
+                uint32_t ua[16], ub[16];
+                tmem_ld16(tl + 16 * m, ua);
+                tmem_ld16(tl + 256 + 16 * m, ub);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int p = 16 * m + i;
+                    if (p >= p_lo && p < p_hi) {
+                        const float c_cur = csj[p * 64];
+                        float c_prev;
+                        if (rev) c_prev = (p == p_hi - 1) ? 0.f : csj[(p + 1) * 64];
+                        else c_prev = (p == p_lo) ? 0.f : csj[(p - 1) * 64];
+                        float* hp = reinterpret_cast<float*>(hb + p * 16);
+                        const float xp = ly == 0 ? __uint_as_float(ub[i]) : *hp;
+                        const float r = sigmoid_from_neg_log2(fmaf(vr, c_prev, (__uint_as_float(ua[i]) + br) * nl2e));
+                        *hp = tf32r(fmaf(r, c_cur - xp, xp));
+                    } else if (p >= p_hi && p < p_end) {
+                        *reinterpret_cast<float*>(hb + p * 16) = 0.f;
+                    }
+                }
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+
+    // ---- ConvTranspose1d: out[positions][64] = sum_kk slab[p + kk] . Wct_kk   (positions on the lanes)
+    if (tid == 0) {
+        for (int gl = 0; gl < 8; ++gl) {
+            const int g = cbeg + gl, slot = g % DF_NSTG;
+            mbar_wait(full_w + slot, (g / DF_NSTG) & 1);
+            tc_fence_after();
+            const uint32_t st = ring_u + slot * DF_WCH;
+#pragma unroll
+            for (int k8 = 0; k8 < 8; ++k8) {
+                const uint64_t db = umma_desc(st + 2 * k8 * 1024, 1024, 128);
+                const uint32_t acc_on = (gl > 0 || k8 > 0) ? 1u : 0u;
+                umma_tf32(tmem, umma_desc(hbuf_u + 2 * k8 * DF_LBO + gl * 16, DF_LBO, 128), db, IDESC_CT, acc_on);
+                umma_tf32(tmem + 64, umma_desc(hbuf_u + 2 * k8 * DF_LBO + (gl + 128) * 16, DF_LBO, 128), db, IDESC_CT, acc_on);
+            }
+            umma_commit(mma_done + slot);
+        }
+        umma_commit(acc_ready);
+    } else if (tid == 32) {
+        produce_until(DF_NCHUNK);
+    }
+    mbar_wait(acc_ready, 0);  // fifth completion of the accumulator barrier
+    tc_fence_after();
+    {
+        const int mt = (warp >> 2) & 1, chalf = warp >> 3;
+        float* stg = cs + warp * (32 * TC_STG_LD);  // 16 x 4608 B: spills from cs into the (drained) weight ring
+        const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 64 + chalf * 32), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(stg + lane * TC_STG_LD + 4 * i) =
+                make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        __syncwarp();
+        const float* resid = a.first ? a.g_first : a.g_in;
+        const float4 bi = ldg4(a.ct_bias + chalf * 32 + c4);
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+            const int r = pp * 4 + rsub;
+            const int off = pos2off[mt * 128 + q * 32 + r];
+            if (off >= 0) {
+                const float4 x = *reinterpret_cast<const float4*>(stg + r * TC_STG_LD + c4);
+                const float4 rr = __ldcg(reinterpret_cast<const float4*>(resid + off + chalf * 32 + c4));
+                *reinterpret_cast<float4*>(a.g_out + off + chalf * 32 + c4) =
+                    make_float4(x.x + bi.x + rr.x, x.y + bi.y + rr.y, x.z + bi.z + rr.z, x.w + bi.w + rr.w);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+inline cudaError_t launch_dprnn_fused(const DfArgs& a, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(dprnn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int tiles = (a.nseq_total + a.nseq_tile - 1) / a.nseq_tile;
+    dprnn_fused_kernel<<<tiles, DF_NT, DF_SMEM, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace rtfs

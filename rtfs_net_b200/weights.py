@@ -32,6 +32,31 @@ def umma_image(w: torch.Tensor) -> torch.Tensor:
     return w.reshape(N, K // 4, 4).permute(1, 0, 2).contiguous()
 
 
+def dprnn_fused_image(w0, wl, ctw):
+    """Weight slabs of the fused dual-path RNN kernel (dprnn_fused.cuh), 52 x 4096 floats.
+    w0 [256][512] and wl[i] [192][64] have rows m*64+col (m: 0 candidate, 1 forget, 2 reset, 3 highway);
+    ctw [64][512] has K = kk*64+ci.  SRU slab (16 K values): [acc 2][K piece 4][lane 128][4] with
+    acc0 lanes = (m0 | m2), acc1 lanes = (m1 | m3 or zeros); conv slab kk: [K piece 16][co 64][4]."""
+    def lanes(w, k):
+        m = [w[i * 64:(i + 1) * 64] for i in range(k)]
+        z = torch.zeros_like(m[0])
+        return torch.cat([m[0], m[2]], 0), torch.cat([m[1], m[3] if k == 4 else z], 0)
+
+    slabs = []
+    for w, k in [(w0, 4)] + [(x, 3) for x in wl]:
+        a0, a1 = lanes(w, k)
+        for g in range(w.shape[1] // 16):
+            for acc in (a0, a1):
+                blk = acc[:, 16 * g:16 * g + 16]  # [128][16]
+                slabs.append(blk.reshape(128, 4, 4).permute(1, 0, 2).reshape(-1))
+    for kk in range(8):
+        blk = ctw[:, 64 * kk:64 * kk + 64]  # [64 co][64]
+        slabs.append(blk.reshape(64, 16, 4).permute(1, 0, 2).reshape(-1))
+    out = torch.cat(slabs).contiguous()
+    assert out.numel() == 52 * 4096
+    return out
+
+
 def _tapmajor(w):
     """depthwise (C,1,4,4) -> [16][C]"""
     C = w.shape[0]
@@ -155,6 +180,8 @@ def prepare(sd, device):
         for l in range(4):
             out[f"RTFS_P_{tag}_WI{l}"] = umma_image(out[f"RTFS_P_{tag}_W{l}"])
         out[f"RTFS_P_{tag}_CTWI"] = umma_image(out[f"RTFS_P_{tag}_CTW"])
+        out[f"RTFS_P_{tag}_FUSED"] = dprnn_fused_image(
+            out[f"RTFS_P_{tag}_W0"], [out[f"RTFS_P_{tag}_W{l}"] for l in (1, 2, 3)], out[f"RTFS_P_{tag}_CTW"])
 
     missing = [n for n in _lib.PARAM_NAMES if n not in out]
     if missing:
