@@ -34,7 +34,7 @@ constexpr int DF_CS = DF_NP * 64 * 4;      // 65536: c_t of every (position, col
 constexpr int DF_WCH = 16384;              // weight slab bytes
 constexpr int DF_NSTG = 5;
 constexpr int DF_NCHUNK = 32 + 3 * 4 + 8;  // layer 0 | layers 1-3 | transposed conv
-constexpr int DF_SMEM = DF_HBUF + DF_CS + DF_NSTG * DF_WCH + DF_NP * 4 + 256;
+constexpr int DF_SMEM = DF_HBUF + DF_CS + DF_NSTG * DF_WCH + DF_NP * 4 + 256 + 8 * 16 * 8;
 
 struct DfArgs {
     const float* g_in;    // (B,Tc,Fc,64) when first == 0
@@ -54,6 +54,7 @@ struct DfArgs {
     int first;
     int S, L;       // sequence length, SRU steps (S - 7)
     int nseq_total, nseq_tile, n_other;
+    long long* dbg;  // optional: [tiles][16] clock64 stamps of thread 0 at the phase boundaries
 };
 
 DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -64,10 +65,72 @@ DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+DEVINL void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-DEVINL float sigmoid_from_neg_log2(float t) {  // t = -x*log2(e)  ->  1/(1+2^t)
-    return __fdividef(1.f, 1.f + exp2f(t));
+constexpr float DF_NL2E = -1.4426950408889634f;
+// MUFU approximations without the denormal fix-ups of exp2f / division: 2^t flushes to 0 / overflows to inf
+// at the ends, which is exactly sigmoid's 1 / 0 limit
+DEVINL float df_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+DEVINL float df_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// one step of c_t = f_t c_{t-1} + (1 - f_t) u0_t, f_t = sigmoid(u1_t + v_f c_{t-1} + b_f); vf and u1 are pre-scaled by -log2(e)
+template <bool PRED>
+DEVINL float df_cstep(float c, float vf, float u1, float u0, float* dst, bool valid) {
+    const float f = df_rcp(1.f + df_ex2(fmaf(vf, c, u1)));
+    const float cn = fmaf(f, c - u0, u0);
+    if (PRED) {
+        if (valid) *dst = cn;
+        return valid ? cn : c;
+    }
+    *dst = cn;
+    return cn;
+}
+
+// h_t = r_t c_t + (1 - r_t) x'_t, r_t = sigmoid(u2_t + v_r c_{t-1} + b_r) for the 16 steps of TMEM column block m.
+// FULL: all 16 steps lie inside [p_lo, p_hi) (no per-step predicates); K4: x' = highway projection (acc1), else the
+// previous layer's h read in place from the slab.  rev: scan order is descending (c_{t-1} is the row above).
+template <bool FULL, bool K4>
+DEVINL void df_hchunk(uint32_t tl, int m, bool rev, int p_lo, int p_hi, int p_end, float vr, float br, const float* csj, unsigned char* hb) {
+    uint32_t ua[16], ub[16];
+    tmem_ld16(tl + 16 * m, ua);
+    if (K4) tmem_ld16(tl + 256 + 16 * m, ub);
+    const int p0 = 16 * m;
+    float cc[18], xp[16];  // cc[i + 1] = c at step p0 + i ; cc[0], cc[17] = neighbours (0 outside the sequence)
+#pragma unroll
+    for (int i = -1; i <= 16; ++i) {
+        const int p = p0 + i;
+        const bool in = FULL ? ((i >= 0 && i < 16) || (p >= p_lo && p < p_hi)) : (p >= p_lo && p < p_hi);
+        cc[i + 1] = in ? csj[p * 64] : 0.f;
+    }
+    if (!K4) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) xp[i] = (FULL || (p0 + i >= p_lo && p0 + i < p_hi)) ? *reinterpret_cast<const float*>(hb + (p0 + i) * 16) : 0.f;
+    }
+    tmem_ld_wait();
+    float hv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float x = K4 ? __uint_as_float(ub[i]) : xp[i];
+        const float cprev = rev ? cc[i + 2] : cc[i];
+        const float r = df_rcp(1.f + df_ex2(fmaf(vr, cprev, (__uint_as_float(ua[i]) + br) * DF_NL2E)));
+        hv[i] = tf32r(fmaf(r, cc[i + 1] - x, x));
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int p = p0 + i;
+        if (FULL || (p >= p_lo && p < p_hi)) *reinterpret_cast<float*>(hb + p * 16) = hv[i];
+        else if (p >= p_hi && p < p_end) *reinterpret_cast<float*>(hb + p * 16) = 0.f;
+    }
 }
 
 __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
@@ -80,11 +143,20 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
     uint64_t* mma_done = full_w + DF_NSTG;
     uint64_t* acc_ready = mma_done + DF_NSTG;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
+    float* seqstat = reinterpret_cast<float*>(tmem_slot + 2);  // [4 sequences][mean, rstd] of the gLN applied when first
+    // chunk_bar[(sequence, direction)][16-step block]: c-recurrence warp -> h warp hand-off, one completion per layer
+    uint64_t* chunk_bar = reinterpret_cast<uint64_t*>(smem_raw + DF_HBUF + DF_CS + DF_NSTG * DF_WCH + DF_NP * 4 + 256);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = warp & 3, sw = warp >> 2;
     const int S = a.S, L = a.L;
     const int seq0 = blockIdx.x * a.nseq_tile;
+    int dbg_i = 0;
+#define DF_STAMP()                                                                  \
+    do {                                                                            \
+        if (a.dbg != nullptr && tid == 0) a.dbg[blockIdx.x * 16 + dbg_i++] = clock64(); \
+    } while (0)
+    DF_STAMP();
 
     if (warp == 0) tmem_alloc<512>(tmem_slot);
     if (tid == 32) {
@@ -94,6 +166,7 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
             mbar_init(mma_done + s, 1);
         }
         mbar_init(acc_ready, 1);
+        for (int i = 0; i < 8 * 16; ++i) mbar_init(chunk_bar + i, 1);
         fence_mbar_init();
     }
     if (tid < DF_NP) {
@@ -108,6 +181,13 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
         }
         pos2off[p] = off;
     }
+    if (a.first && tid >= 64 && tid < 68) {
+        const int seqg = seq0 + (tid - 64);
+        float mean = 0.f, rstd = 0.f;
+        if (seqg < a.nseq_total) gln_mean_rstd(a.gln.sums, seqg / a.n_other, a.gln.inv_n, mean, rstd);
+        seqstat[2 * (tid - 64)] = mean;
+        seqstat[2 * (tid - 64) + 1] = rstd;
+    }
     // guard rows (7 before, 7 after) of every 4-channel piece
     for (int i = tid; i < 14 * 16; i += DF_NT) {
         const int kq = i / 14, rr = i - kq * 14;
@@ -118,6 +198,7 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    DF_STAMP();
 
     // ---- weight producer (thread 32): slab g -> ring slot g % 5
     int wnext = 0;
@@ -133,60 +214,62 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
     };
     if (tid == 32) produce_until(DF_NSTG);
 
-    // ---- P0: g -> LayerNorm over C -> n (tf32) into the slab   (two batches of 4 rows per thread)
+    // ---- P0: g -> LayerNorm over C -> n (tf32) into the slab; all 8 rows of a thread are in flight together
     {
         const int l16 = tid & 15, c = l16 * 4;
         const float4 gm = ldg4(a.ln_gamma + c), be = ldg4(a.ln_beta + c);
-#pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
-            float4 v[4], pl[4];
-            int offs[4];
+        float4 v[8], plv[8];
+        int offs[8];
+        const float* src = a.first ? a.d1_pre : a.g_in;
+        const float* src2 = a.first ? a.pool : a.g_in;  // second stream only read when first
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-                const int p = (hh * 4 + it) * 32 + (tid >> 4);
-                offs[it] = pos2off[p];
-                v[it] = pl[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int it = 0; it < 8; ++it) {
+            const int p = it * 32 + (tid >> 4);
+            offs[it] = pos2off[p];
+            v[it] = plv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (offs[it] >= 0) {
+                v[it] = ldg4(src + offs[it] + c);
+                if (a.first) plv[it] = ldg4(src2 + offs[it] + c);
+            }
+        }
+        if (a.first) {  // g = gLN(d1_pre) + pool, written out as the residual / next stage input
+            const float4 gg = ldg4(a.gln.gamma + c), gb = ldg4(a.gln.beta + c);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
                 if (offs[it] >= 0) {
-                    if (a.first) {
-                        v[it] = ldg4(a.d1_pre + offs[it] + c);
-                        pl[it] = ldg4(a.pool + offs[it] + c);
-                    } else {
-                        v[it] = ldg4(a.g_in + offs[it] + c);
-                    }
-                }
-            }
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-                const int p = (hh * 4 + it) * 32 + (tid >> 4);
-                float4 x = v[it];
-                if (a.first && offs[it] >= 0) {
-                    const int b = offs[it] / (a.Tc * a.Fc * 64);
-                    float mean, rstd;
-                    gln_mean_rstd(a.gln.sums, b, a.gln.inv_n, mean, rstd);
-                    const float4 gg = ldg4(a.gln.gamma + c), gb = ldg4(a.gln.beta + c);
-                    x.x = (x.x - mean) * rstd * gg.x + gb.x + pl[it].x;
-                    x.y = (x.y - mean) * rstd * gg.y + gb.y + pl[it].y;
-                    x.z = (x.z - mean) * rstd * gg.z + gb.z + pl[it].z;
-                    x.w = (x.w - mean) * rstd * gg.w + gb.w + pl[it].w;
+                    const float4 pl = plv[it];
+                    const int sq = (it * 32 + (tid >> 4)) / S;
+                    const float mean = seqstat[2 * sq], rstd = seqstat[2 * sq + 1];
+                    float4 x = v[it];
+                    x.x = (x.x - mean) * rstd * gg.x + gb.x + pl.x;
+                    x.y = (x.y - mean) * rstd * gg.y + gb.y + pl.y;
+                    x.z = (x.z - mean) * rstd * gg.z + gb.z + pl.z;
+                    x.w = (x.w - mean) * rstd * gg.w + gb.w + pl.w;
                     *reinterpret_cast<float4*>(a.g_first + offs[it] + c) = x;
+                    v[it] = x;
                 }
-                float s = x.x + x.y + x.z + x.w;
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                const float mu = s * (1.f / 64.f);
-                const float dx = x.x - mu, dy = x.y - mu, dz = x.z - mu, dw = x.w - mu;
-                float qq = dx * dx + dy * dy + dz * dz + dw * dw;
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
-                const float rs = 1.f / sqrtf(qq * (1.f / 64.f) + RTFS_EPS);
-                float4 n;
-                n.x = tf32r(dx * rs * gm.x + be.x);
-                n.y = tf32r(dy * rs * gm.y + be.y);
-                n.z = tf32r(dz * rs * gm.z + be.z);
-                n.w = tf32r(dw * rs * gm.w + be.w);
-                if (offs[it] < 0) n = make_float4(0.f, 0.f, 0.f, 0.f);
-                *reinterpret_cast<float4*>(hbuf + l16 * DF_LBO + (7 + p) * 16) = n;
             }
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int p = it * 32 + (tid >> 4);
+            const float4 x = v[it];
+            float s = x.x + x.y + x.z + x.w;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mu = s * (1.f / 64.f);
+            const float dx = x.x - mu, dy = x.y - mu, dz = x.z - mu, dw = x.w - mu;
+            float qq = dx * dx + dy * dy + dz * dz + dw * dw;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+            const float rs = rsqrtf(qq * (1.f / 64.f) + RTFS_EPS);
+            float4 n;
+            n.x = tf32r(dx * rs * gm.x + be.x);
+            n.y = tf32r(dy * rs * gm.y + be.y);
+            n.z = tf32r(dz * rs * gm.z + be.z);
+            n.w = tf32r(dw * rs * gm.w + be.w);
+            if (offs[it] < 0) n = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(hbuf + l16 * DF_LBO + (7 + p) * 16) = n;
         }
     }
     fence_proxy_async();
@@ -194,6 +277,7 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
     __syncthreads();
     tc_fence_after();
 
+    DF_STAMP();
     const uint32_t hbuf_u = smem_u32(hbuf);
     const uint32_t ring_u = smem_u32(wring);
     constexpr uint32_t IDESC_SRU = umma_idesc_tf32(128, 256);
@@ -230,89 +314,80 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
         cbeg += nch;
         mbar_wait(acc_ready, ly & 1);
         tc_fence_after();
+        DF_STAMP();
 
         // ---- c-recurrence: warps q = 0 (forward columns 0-31) and q = 1 (backward columns 32-63)
         if (q < 2 && seq_on) {
             const int j = q * 32 + lane;
-            const float nl2e = -1.4426950408889634f;
-            const float vf = __ldg(a.wc[ly] + j) * nl2e, bf = __ldg(a.bias[ly] + j);
+            const float vf = __ldg(a.wc[ly] + j) * DF_NL2E, bf = __ldg(a.bias[ly] + j);
             const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
             float c = 0.f;
             float* csj = cs + j;
-            if (q == 0) {
-                for (int m = p_lo >> 4; m <= (p_hi - 1) >> 4; ++m) {
-                    uint32_t ua[16], ub[16];
-                    tmem_ld16(tl + 16 * m, ua);
-                    tmem_ld16(tl + 256 + 16 * m, ub);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int p = 16 * m + i;
-                        if (p >= p_lo && p < p_hi) {
-                            const float u0 = __uint_as_float(ua[i]);
-                            const float f = sigmoid_from_neg_log2(fmaf(vf, c, (__uint_as_float(ub[i]) + bf) * nl2e));
-                            c = fmaf(f, c - u0, u0);
-                            csj[p * 64] = c;
-                        }
-                    }
-                }
-            } else {
-                for (int m = (p_hi - 1) >> 4; m >= p_lo >> 4; --m) {
-                    uint32_t ua[16], ub[16];
-                    tmem_ld16(tl + 16 * m, ua);
-                    tmem_ld16(tl + 256 + 16 * m, ub);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 15; i >= 0; --i) {
-                        const int p = 16 * m + i;
-                        if (p >= p_lo && p < p_hi) {
-                            const float u0 = __uint_as_float(ua[i]);
-                            const float f = sigmoid_from_neg_log2(fmaf(vf, c, (__uint_as_float(ub[i]) + bf) * nl2e));
-                            c = fmaf(f, c - u0, u0);
-                            csj[p * 64] = c;
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        // ---- h: warps q = 2 (columns 0-31) and q = 3 (columns 32-63), every step independent
-        if (q >= 2 && seq_on) {
-            const int j = (q - 2) * 32 + lane;
-            const bool rev = q == 3;
-            const float nl2e = -1.4426950408889634f;
-            const float vr = __ldg(a.wc[ly] + 64 + j) * nl2e, br = __ldg(a.bias[ly] + 64 + j);
-            const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
-            unsigned char* hb = hbuf + (j >> 2) * DF_LBO + 7 * 16 + (j & 3) * 4;
-            const float* csj = cs + j;
-            const int p_end = ly == 3 ? p_lo + S : p_hi;  // the last layer also zeroes the 7 tail rows (conv-transpose padding)
-            for (int m = p_lo >> 4; m <= (p_end - 1) >> 4; ++m) {
+            const int m_lo = p_lo >> 4, m_hi = (p_hi - 1) >> 4;
+            for (int mm = m_lo; mm <= m_hi; ++mm) {
+                const int m = q == 0 ? mm : m_lo + m_hi - mm;
                 uint32_t ua[16], ub[16];
                 tmem_ld16(tl + 16 * m, ua);
                 tmem_ld16(tl + 256 + 16 * m, ub);
                 tmem_ld_wait();
+                float u1[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int p = 16 * m + i;
-                    if (p >= p_lo && p < p_hi) {
-                        const float c_cur = csj[p * 64];
-                        float c_prev;
-                        if (rev) c_prev = (p == p_hi - 1) ? 0.f : csj[(p + 1) * 64];
-                        else c_prev = (p == p_lo) ? 0.f : csj[(p - 1) * 64];
-                        float* hp = reinterpret_cast<float*>(hb + p * 16);
-                        const float xp = ly == 0 ? __uint_as_float(ub[i]) : *hp;
-                        const float r = sigmoid_from_neg_log2(fmaf(vr, c_prev, (__uint_as_float(ua[i]) + br) * nl2e));
-                        *hp = tf32r(fmaf(r, c_cur - xp, xp));
-                    } else if (p >= p_hi && p < p_end) {
-                        *reinterpret_cast<float*>(hb + p * 16) = 0.f;
+                for (int i = 0; i < 16; ++i) u1[i] = (__uint_as_float(ub[i]) + bf) * DF_NL2E;  // off the serial chain
+                const bool full = 16 * m >= p_lo && 16 * m + 16 <= p_hi;
+                if (q == 0) {
+                    if (full) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) c = df_cstep<false>(c, vf, u1[i], __uint_as_float(ua[i]), csj + (16 * m + i) * 64, true);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            c = df_cstep<true>(c, vf, u1[i], __uint_as_float(ua[i]), csj + (16 * m + i) * 64, 16 * m + i >= p_lo && 16 * m + i < p_hi);
                     }
+                } else {
+                    if (full) {
+#pragma unroll
+                        for (int i = 15; i >= 0; --i) c = df_cstep<false>(c, vf, u1[i], __uint_as_float(ua[i]), csj + (16 * m + i) * 64, true);
+                    } else {
+#pragma unroll
+                        for (int i = 15; i >= 0; --i)
+                            c = df_cstep<true>(c, vf, u1[i], __uint_as_float(ua[i]), csj + (16 * m + i) * 64, 16 * m + i >= p_lo && 16 * m + i < p_hi);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(chunk_bar + (sw * 2 + q) * 16 + m);  // release: this block's c values are in shared memory
+            }
+        }
+        DF_STAMP();
+        // ---- h: warps q = 2 (columns 0-31) and q = 3 (columns 32-63); every step is independent, so each
+        //      16-step batch is loaded, computed and stored as a block (no load waits behind a store)
+        if (a.dbg != nullptr && tid == 64) a.dbg[(gridDim.x + blockIdx.x) * 16 + 2 * ly] = clock64();
+        if (q >= 2 && seq_on) {
+            const int j = (q - 2) * 32 + lane;
+            const float vr = __ldg(a.wc[ly] + 64 + j) * DF_NL2E, br = __ldg(a.bias[ly] + 64 + j);
+            const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+            unsigned char* hb = hbuf + (j >> 2) * DF_LBO + 7 * 16 + (j & 3) * 4;
+            const float* csj = cs + j;
+            const int p_end = ly == 3 ? p_lo + S : p_hi;  // the last layer also zeroes the 7 tail rows (conv-transpose padding)
+            const int m_lo = p_lo >> 4, m_hi = (p_end - 1) >> 4, m_chi = (p_hi - 1) >> 4;
+            for (int mm = m_lo; mm <= m_hi; ++mm) {
+                const int m = q == 2 ? mm : m_lo + m_hi - mm;  // follow the c-recurrence's block order
+                if (m <= m_chi) mbar_wait(chunk_bar + (sw * 2 + (q - 2)) * 16 + m, ly & 1);
+                const bool full = 16 * m >= p_lo && 16 * m + 16 <= p_hi;
+                if (full) {
+                    if (ly == 0) df_hchunk<true, true>(tl, m, q == 3, p_lo, p_hi, p_end, vr, br, csj, hb);
+                    else df_hchunk<true, false>(tl, m, q == 3, p_lo, p_hi, p_end, vr, br, csj, hb);
+                } else {
+                    if (ly == 0) df_hchunk<false, true>(tl, m, q == 3, p_lo, p_hi, p_end, vr, br, csj, hb);
+                    else df_hchunk<false, false>(tl, m, q == 3, p_lo, p_hi, p_end, vr, br, csj, hb);
                 }
             }
         }
+        if (a.dbg != nullptr && tid == 64) a.dbg[(gridDim.x + blockIdx.x) * 16 + 2 * ly + 1] = clock64();
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
+        DF_STAMP();
     }
 
     // ---- ConvTranspose1d: out[positions][64] = sum_kk slab[p + kk] . Wct_kk   (positions on the lanes)
@@ -337,6 +412,7 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
     }
     mbar_wait(acc_ready, 0);  // fifth completion of the accumulator barrier
     tc_fence_after();
+    DF_STAMP();
     {
         const int mt = (warp >> 2) & 1, chalf = warp >> 3;
         float* stg = cs + warp * (32 * TC_STG_LD);  // 16 x 4608 B: spills from cs into the (drained) weight ring
@@ -364,6 +440,8 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
     }
     tc_fence_before();
     __syncthreads();
+    DF_STAMP();
+#undef DF_STAMP
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
