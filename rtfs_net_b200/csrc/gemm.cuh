@@ -23,8 +23,8 @@ constexpr int gemm_smem_floats(int extra) {
 
 // Per-CTA table of gLN scale/shift for the (at most two) samples a 128-row tile touches.
 // tab layout: [2 samples][C][2]  (sc, sh):  y = x*sc + sh
-DEVINL void fill_gln_table(float* tab, const GlnRef& r, int b_first, int B, int C) {
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+DEVINL void fill_gln_table(float* tab, const GlnRef& r, int b_first, int B, int C, int tid = threadIdx.x, int nthr = blockDim.x) {
+    for (int i = tid; i < 2 * C; i += nthr) {
         const int s = i / C, c = i - s * C;
         const int b = b_first + s;
         float sc = 0.f, sh = 0.f;
@@ -77,10 +77,23 @@ struct GlnActLoader {
         row0_ = row0 + (threadIdx.x >> 3);
         M_ = M;
     }
+    // producer-group variant (persistent kernel): ptid in [0, nthr)
+    DEVINL void init_p(int row0, int M, float* extra, int ptid, int nthr) {
+        bfirst_ = row0 / P;
+        split_ = (bfirst_ + 1) * P;
+        fill_gln_table(extra, gln, bfirst_, B, C, ptid, nthr);
+        tab_ = extra;
+        row0_ = row0 + (ptid >> 3);
+        M_ = M;
+    }
     DEVINL float4 load(int i, int k) const {
         const int row = row0_ + 32 * i;
         if (row >= M_) return make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 x = ldg4(A + (long long)row * C + k);
+        return xform(ldg4(A + (long long)row * C + k), row, k);
+    }
+    DEVINL const float* raw(long long row, int k) const { return A + row * C + k; }
+    // transform of a raw float4 at (row, k..k+3); valid after init/init_p of the row's tile
+    DEVINL float4 xform(float4 x, int row, int k) const {
         const int s = row >= split_ ? 1 : 0;
         const float* tb = tab_ + 2 * (s * C + k);
         const float4 t0 = *reinterpret_cast<const float4*>(tb);
@@ -115,10 +128,18 @@ struct GateLoader {
         M_ = M;
         a_ = __ldg(slope);
     }
+    DEVINL void init_p(int row0, int M, float*, int ptid, int) {
+        row0_ = row0 + (ptid >> 3);
+        M_ = M;
+        a_ = __ldg(slope);
+    }
     DEVINL float4 load(int i, int k) const {
         const int row = row0_ + 32 * i;
         if (row >= M_) return make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 x = ldg4(A + (long long)row * C + k);
+        return xform(ldg4(A + (long long)row * C + k), row, k);
+    }
+    DEVINL const float* raw(long long row, int k) const { return A + row * C + k; }
+    DEVINL float4 xform(float4 x, int, int k) const {
         const float4 w = ldg4(wg + k), b = ldg4(bg + k);
         float4 y;
         y.x = prelu(fmaf(w.x, x.x, b.x), a_);
@@ -142,10 +163,18 @@ struct PreluLoader {
         M_ = M;
         a_ = __ldg(slope);
     }
+    DEVINL void init_p(int row0, int M, float*, int ptid, int) {
+        row0_ = row0 + (ptid >> 3);
+        M_ = M;
+        a_ = __ldg(slope);
+    }
     DEVINL float4 load(int i, int k) const {
         const int row = row0_ + 32 * i;
         if (row >= M_) return make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 x = ldg4(A + (long long)row * C + k);
+        return xform(ldg4(A + (long long)row * C + k), row, k);
+    }
+    DEVINL const float* raw(long long row, int k) const { return A + row * C + k; }
+    DEVINL float4 xform(float4 x, int, int) const {
         x.x = prelu(x.x, a_);
         x.y = prelu(x.y, a_);
         x.z = prelu(x.z, a_);
@@ -169,15 +198,16 @@ struct TfarLoader {
     const float* tab_;
     long long offc_[4];
     int s_[4];
-    DEVINL void init(int row0, int M, float* extra) {
+    DEVINL void init(int row0, int M, float* extra) { init_p(row0, M, extra, threadIdx.x, blockDim.x); }
+    DEVINL void init_p(int row0, int M, float* extra, int ptid, int nthr) {
         P_ = T * F;
         bfirst_ = row0 / P_;
-        fill_gln_table(extra, n_l, bfirst_, B, 64);
-        fill_gln_table(extra + 256, n_d, bfirst_, B, 64);
-        fill_gln_table(extra + 512, n_g, bfirst_, B, 64);
-        fill_gln_table(extra + 768, n_e, bfirst_, B, 64);
+        fill_gln_table(extra, n_l, bfirst_, B, 64, ptid, nthr);
+        fill_gln_table(extra + 256, n_d, bfirst_, B, 64, ptid, nthr);
+        fill_gln_table(extra + 512, n_g, bfirst_, B, 64, ptid, nthr);
+        fill_gln_table(extra + 768, n_e, bfirst_, B, 64, ptid, nthr);
         tab_ = extra;
-        row0_ = row0 + (threadIdx.x >> 3);
+        row0_ = row0 + (ptid >> 3);
         M_ = M;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {

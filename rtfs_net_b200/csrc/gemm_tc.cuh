@@ -92,6 +92,15 @@ DEVINL void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {  // no wait: pair with tcgen05.wait::ld
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+
 // UMMA shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor, version 1):
 //   [0,14) start>>4 | [16,30) leading (K-direction core-matrix) byte offset>>4 | [32,46) stride (8-row group) byte offset>>4
 DEVINL uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -102,20 +111,51 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+DEVINL void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// (sum, sumsq) of a thread group synchronised by a named barrier -> one fp64 atomic pair
+DEVINL void group_stats_atomic(float s, float ss, double* dst, float* scratch, int gtid, int nthr, int barid) {
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    const int lane = gtid & 31, w = gtid >> 5, nw = nthr >> 5;
+    named_bar_sync(barid, nthr);
+    if (lane == 0) {
+        scratch[2 * w] = s;
+        scratch[2 * w + 1] = ss;
+    }
+    named_bar_sync(barid, nthr);
+    if (w == 0) {
+        float a = lane < nw ? scratch[2 * lane] : 0.f;
+        float b = lane < nw ? scratch[2 * lane + 1] : 0.f;
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if (lane == 0 && dst != nullptr) {
+            atomicAdd(dst, (double)a);
+            atomicAdd(dst + 1, (double)b);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------- float4 epilogues
-// contract: init(row0, M) ; store4(row, col, v) for columns col..col+3 of an in-range row ; finish(scratch)
+// contract: init(row0, M) ; pre = load(row, col) fetches what the row piece needs from global memory (all loads of a
+//           batch of rows are issued before the first store, so they overlap instead of serialising behind the
+//           stores) ; store4(row, col, v, pre) for columns col..col+3 of an in-range row ; finish(scratch)
+struct NoPre {};
 DEVINL float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 struct StoreEpi4 {
     float* C;
     long long ldc;
     const float* bias;  // may be null
+    using Pre = NoPre;
     DEVINL void init(int, int) {}
-    DEVINL void store4(int row, int col, float4 v) {
+    DEVINL Pre load(int, int) const { return Pre{}; }
+    DEVINL void store4(int row, int col, float4 v, const Pre&) {
         if (bias) v = add4(v, ldg4(bias + col));
         *reinterpret_cast<float4*>(C + (long long)row * ldc + col) = v;
     }
     DEVINL void finish(float*) {}
+    DEVINL void finish_group(float*, int, int, int) {}
 };
 
 struct StatsEpi4 {
@@ -131,7 +171,9 @@ struct StatsEpi4 {
         split_ = (bfirst_ + 1) * P;
         s0_ = q0_ = s1_ = q1_ = 0.f;
     }
-    DEVINL void store4(int row, int col, float4 v) {
+    using Pre = NoPre;
+    DEVINL Pre load(int, int) const { return Pre{}; }
+    DEVINL void store4(int row, int col, float4 v, const Pre&) {
         if (bias) v = add4(v, ldg4(bias + col));
         *reinterpret_cast<float4*>(C + (long long)row * ldc + col) = v;
         const float s = (v.x + v.y) + (v.z + v.w);
@@ -148,6 +190,10 @@ struct StatsEpi4 {
         block_stats_atomic(s0_, q0_, sums + 2 * bfirst_, scratch);
         block_stats_atomic(s1_, q1_, (bfirst_ + 1 < B) ? sums + 2 * (bfirst_ + 1) : nullptr, scratch);
     }
+    DEVINL void finish_group(float* scratch, int gtid, int nthr, int barid) {
+        group_stats_atomic(s0_, q0_, sums + 2 * bfirst_, scratch, gtid, nthr, barid);
+        group_stats_atomic(s1_, q1_, (bfirst_ + 1 < B) ? sums + 2 * (bfirst_ + 1) : nullptr, scratch, gtid, nthr, barid);
+    }
 };
 
 // residual_conv epilogue (tdanet.py:131): out = acc + bias + gateway(x) [+ a1 -> next block input]
@@ -160,18 +206,28 @@ struct ResidOutEpi4 {
     const float* slope;
     const float* a1;  // may be null
     float a_;
+    struct Pre {
+        float4 x, a1;
+    };
     DEVINL void init(int, int) { a_ = __ldg(slope); }
-    DEVINL void store4(int row, int col, float4 v) {
+    DEVINL Pre load(int row, int col) const {
         const long long o = (long long)row * 256 + col;
-        const float4 xx = ldg4(x + o), w = ldg4(wg + col), b = ldg4(bg + col), bi = ldg4(bias + col);
-        v.x += bi.x + prelu(fmaf(w.x, xx.x, b.x), a_);
-        v.y += bi.y + prelu(fmaf(w.y, xx.y, b.y), a_);
-        v.z += bi.z + prelu(fmaf(w.z, xx.z, b.z), a_);
-        v.w += bi.w + prelu(fmaf(w.w, xx.w, b.w), a_);
-        if (a1) v = add4(v, ldg4(a1 + o));
+        Pre p;
+        p.x = ldg4(x + o);
+        p.a1 = a1 ? ldg4(a1 + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+        return p;
+    }
+    DEVINL void store4(int row, int col, float4 v, const Pre& p) {
+        const long long o = (long long)row * 256 + col;
+        const float4 w = ldg4(wg + col), b = ldg4(bg + col), bi = ldg4(bias + col);
+        v.x += bi.x + prelu(fmaf(w.x, p.x.x, b.x), a_) + p.a1.x;
+        v.y += bi.y + prelu(fmaf(w.y, p.x.y, b.y), a_) + p.a1.y;
+        v.z += bi.z + prelu(fmaf(w.z, p.x.z, b.z), a_) + p.a1.z;
+        v.w += bi.w + prelu(fmaf(w.w, p.x.w, b.w), a_) + p.a1.w;
         *reinterpret_cast<float4*>(out + o) = v;
     }
     DEVINL void finish(float*) {}
+    DEVINL void finish_group(float*, int, int, int) {}
 };
 
 // S^3 mask epilogue (mask_generator.py:67-99); GEMM columns interleaved on the host: col 2c = real-half
@@ -180,17 +236,28 @@ struct MaskEpi4 {
     float* z;
     const float* bias;
     const float* a0;
+    struct Pre {
+        float2 er, ei;
+    };
     DEVINL void init(int, int) {}
-    DEVINL void store4(int row, int col, float4 v) {
+    DEVINL Pre load(int row, int col) const {
+        const long long o = (long long)row * 256 + (col >> 1);
+        Pre p;
+        p.er = ldg2(a0 + o);
+        p.ei = ldg2(a0 + o + 128);
+        return p;
+    }
+    DEVINL void store4(int row, int col, float4 v, const Pre& p) {
         const float4 bi = ldg4(bias + col);
         const float mr0 = fmaxf(v.x + bi.x, 0.f), mi0 = fmaxf(v.y + bi.y, 0.f);
         const float mr1 = fmaxf(v.z + bi.z, 0.f), mi1 = fmaxf(v.w + bi.w, 0.f);
         const long long o = (long long)row * 256 + (col >> 1);
-        const float2 er = ldg2(a0 + o), ei = ldg2(a0 + o + 128);
+        const float2 er = p.er, ei = p.ei;
         *reinterpret_cast<float2*>(z + o) = make_float2(er.x * mr0 - ei.x * mi0, er.y * mr1 - ei.y * mi1);
         *reinterpret_cast<float2*>(z + o + 128) = make_float2(er.x * mi0 + ei.x * mr0, er.y * mi1 + ei.y * mr1);
     }
     DEVINL void finish(float*) {}
+    DEVINL void finish_group(float*, int, int, int) {}
 };
 
 // ConvTranspose1d-as-GEMM epilogue of the dual-path RNN (rnn_layers.py:153-160)
@@ -199,17 +266,31 @@ struct ConvTEpi4 {
     const float* resid;
     const float* bias;
     int S, n_other, time_path, Tc, Fc;
+    struct Pre {
+        float4 r;
+        long long off;  // < 0: padding row, nothing to store
+    };
     DEVINL void init(int, int) {}
-    DEVINL void store4(int row, int col, float4 v) {
+    DEVINL Pre load(int row, int col) const {
+        Pre p;
         const int seq = row / (S + 7), s = row - seq * (S + 7);
-        if (s >= S) return;
-        const int b = seq / n_other, o = seq - b * n_other;
-        const int t = time_path ? s : o, f = time_path ? o : s;
-        const long long off = ((((long long)b * Tc + t) * Fc) + f) * 64 + col;
-        v = add4(add4(v, ldg4(bias + col)), ldg4(resid + off));
-        *reinterpret_cast<float4*>(out + off) = v;
+        p.off = -1;
+        p.r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s < S) {
+            const int b = seq / n_other, o = seq - b * n_other;
+            const int t = time_path ? s : o, f = time_path ? o : s;
+            p.off = ((((long long)b * Tc + t) * Fc) + f) * 64 + col;
+            p.r = ldg4(resid + p.off);
+        }
+        return p;
+    }
+    DEVINL void store4(int, int col, float4 v, const Pre& p) {
+        if (p.off < 0) return;
+        v = add4(add4(v, ldg4(bias + col)), p.r);
+        *reinterpret_cast<float4*>(out + p.off) = v;
     }
     DEVINL void finish(float*) {}
+    DEVINL void finish_group(float*, int, int, int) {}
 };
 
 // ---------------------------------------------------------------------------------- kernel
@@ -232,9 +313,10 @@ __host__ __device__ constexpr int tc_smem_bytes(int extra_floats) {
     return (tc_stage_bytes<BN, NS>() > TC_STG_BYTES ? tc_stage_bytes<BN, NS>() : TC_STG_BYTES) + extra_floats * 4 + 256 + 128;
 }
 
-template <int BN, int KTOT, int NS, int MINB, class AL, class EP>
+template <int BN, int KTOT, int NS, int MINB, int PF, class AL, class EP>
 __global__ void __launch_bounds__(TC_THREADS, MINB) gemm_tc_kernel(AL al, const float* __restrict__ Wimg, EP ep, int M) {
     constexpr int NK = KTOT / TC_KC;
+    static_assert(PF >= 1 && PF <= 4, "A-operand register prefetch depth (chunks in flight per thread)");
     constexpr int WBYTES = BN * 128;
     constexpr int TCOLS = tc_tmem_cols<BN>();
     constexpr int PD = (NK <= NS) ? NK : NS - 2;  // W chunks in flight ahead of the A producer
@@ -287,12 +369,11 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) gemm_tc_kernel(AL al, const 
     unsigned char* a_dst0 = a_stage + kq * TC_LBO_A + (tid >> 3) * 16;
     constexpr uint32_t IDESC = umma_idesc_tf32(TC_BM, BN);
 
-    float4 areg[2][4];
+    float4 areg[PF][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) areg[0][i] = al.load(i, kq * 4);
-    if (NK > 1) {
+    for (int c = 0; c < PF && c < NK; ++c) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) areg[1][i] = al.load(i, TC_KC + kq * 4);
+        for (int i = 0; i < 4; ++i) areg[c][i] = al.load(i, c * TC_KC + kq * 4);
     }
 
 #pragma unroll
@@ -306,16 +387,16 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) gemm_tc_kernel(AL al, const 
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            float4 v = areg[kc & 1][i];
+            float4 v = areg[kc % PF][i];
             v.x = tf32r(v.x);
             v.y = tf32r(v.y);
             v.z = tf32r(v.z);
             v.w = tf32r(v.w);
             *reinterpret_cast<float4*>(a_dst0 + (size_t)s * TC_A_STAGE + i * (32 * 16)) = v;
         }
-        if (kc + 2 < NK) {
+        if (kc + PF < NK) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) areg[kc & 1][i] = al.load(i, (kc + 2) * TC_KC + kq * 4);
+            for (int i = 0; i < 4; ++i) areg[kc % PF][i] = al.load(i, (kc + PF) * TC_KC + kq * 4);
         }
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
         __syncthreads();
@@ -345,19 +426,31 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) gemm_tc_kernel(AL al, const 
 #pragma unroll 1
         for (int cb = 0; cb < BN / 64; ++cb) {
             const int col0 = hlf * (BN / 2) + cb * 32;
-            uint32_t v[32];
-            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
+            // all global loads of this 32x32 block are issued first and stay in flight while the
+            // accumulator block is read from TMEM and transposed through shared memory
+            typename EP::Pre pre[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                *reinterpret_cast<float4*>(stg + lane * TC_STG_LD + 4 * i) =
-                    make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            for (int p = 0; p < 8; ++p) {
+                const int row = row0 + q * 32 + p * 4 + rsub;
+                pre[p] = ep.load(row < M ? row : M - 1, col0 + c4);
+            }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t v[16];
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0 + 16 * hh, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    *reinterpret_cast<float4*>(stg + lane * TC_STG_LD + 16 * hh + 4 * i) =
+                        make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            }
             __syncwarp();
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
                 const int r = p * 4 + rsub;
                 const float4 x = *reinterpret_cast<const float4*>(stg + r * TC_STG_LD + c4);
                 const int row = row0 + q * 32 + r;
-                if (row < M) ep.store4(row, col0 + c4, x);
+                if (row < M) ep.store4(row, col0 + c4, x, pre[p]);
             }
             __syncwarp();
         }
@@ -467,19 +560,31 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) gemm_tc_unfold_kernel(const 
 #pragma unroll 1
         for (int cb = 0; cb < BN / 64; ++cb) {
             const int col0 = hlf * (BN / 2) + cb * 32;
-            uint32_t v[32];
-            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
+            // all global loads of this 32x32 block are issued first and stay in flight while the
+            // accumulator block is read from TMEM and transposed through shared memory
+            typename EP::Pre pre[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                *reinterpret_cast<float4*>(stg + lane * TC_STG_LD + 4 * i) =
-                    make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            for (int p = 0; p < 8; ++p) {
+                const int row = row0 + q * 32 + p * 4 + rsub;
+                pre[p] = ep.load(row < M ? row : M - 1, col0 + c4);
+            }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t v[16];
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0 + 16 * hh, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    *reinterpret_cast<float4*>(stg + lane * TC_STG_LD + 16 * hh + 4 * i) =
+                        make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            }
             __syncwarp();
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
                 const int r = p * 4 + rsub;
                 const float4 x = *reinterpret_cast<const float4*>(stg + r * TC_STG_LD + c4);
                 const int row = row0 + q * 32 + r;
-                if (row < M) ep.store4(row, col0 + c4, x);
+                if (row < M) ep.store4(row, col0 + c4, x, pre[p]);
             }
             __syncwarp();
         }
@@ -504,9 +609,9 @@ inline cudaError_t launch_gemm_tc_unfold(const float* X, const float* Wimg, cons
     return cudaGetLastError();
 }
 
-template <int BN, int KTOT, int NS, int MINB, class AL, class EP>
+template <int BN, int KTOT, int NS, int MINB, int PF, class AL, class EP>
 inline cudaError_t launch_gemm_tc(const AL& al, const float* Wimg, const EP& ep, int M, cudaStream_t st) {
-    auto kern = gemm_tc_kernel<BN, KTOT, NS, MINB, AL, EP>;
+    auto kern = gemm_tc_kernel<BN, KTOT, NS, MINB, PF, AL, EP>;
     const int smem = tc_smem_bytes<BN, NS>(AL::kExtra);
     static bool configured = false;  // one flag per instantiation
     if (!configured) {

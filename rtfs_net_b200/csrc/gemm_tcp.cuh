@@ -1,0 +1,287 @@
+// Persistent, warp-specialised tcgen05 GEMM for the full-resolution 1x1 convolutions of the RTFS-Net forward
+// (audio bottleneck, gateway+projection, residual conv, S^3 mask): the HBM-bound contractions whose A operand
+// and epilogue each stream a (B*T*F) x 256 fp32 tensor.  Same math, operand layouts, loader and epilogue functors
+// as gemm_tc.cuh; what changes is the schedule: one CTA per SM loops over 128-row tiles with three groups of
+// warps running concurrently, so the loads of tile i+1, the MMAs of tile i and the epilogue traffic of tile i-1
+// are all in flight at once:
+//
+//   warps 0-7   epilogue : tmem_full[acc] -> tcgen05.ld -> shared-memory transpose -> functor (batched global loads,
+//                          coalesced float4 stores) -> tmem_empty[acc]          (two TMEM accumulators, ping-pong)
+//   warps 8-15  producers: loader functor (fused prologue) -> TF32 -> UMMA K-major slab in an NSA-stage ring ->
+//                          full_a[stage]; a stage is recycled when the MMAs that read it commit to empty_a[stage]
+//   warp 16     MMA      : one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) x 4 per K chunk
+//   warp 17     weights  : WRES: the whole image (<= 64 KB) is bulk-copied once and stays resident;
+//                          otherwise 32-wide K slabs stream through an NSW-stage ring (cp.async.bulk + mbarrier)
+#pragma once
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+namespace rtfs {
+
+constexpr int TCP_THREADS = 576;
+constexpr int TCP_EPI = 256, TCP_PROD = 256;
+
+DEVINL void mbar_arrive_cta(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN, int KTOT, int NSA, int NSW, bool WRES>
+__host__ __device__ constexpr int tcp_smem_bytes(int extra_floats) {
+    return NSA * TC_A_STAGE + (WRES ? (KTOT / TC_KC) : NSW) * BN * 128 + TC_STG_BYTES + 2 * extra_floats * 4 + 512;
+}
+
+// EPS: epilogue functor exposes finish_group(scratch, gtid, nthr, barid) (gLN statistics) instead of finish()
+// ASYNC: the producers land the raw A chunk in its ring stage with 16-byte cp.async (NSA-2 chunks = ~100 KB in flight
+// per SM, no registers tied up, running ahead across tile boundaries) and apply the loader's transform in place.
+template <int BN, int KTOT, int NSA, int NSW, bool WRES, int PF, bool ASYNC, class AL, class EP>
+__global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(AL al, const float* __restrict__ Wimg, EP ep, int M, int ntiles) {
+    constexpr int NK = KTOT / TC_KC;
+    constexpr int WBYTES = BN * 128;
+    constexpr int NWS = WRES ? NK : NSW;  // weight slabs held in shared memory
+    static_assert(2 * BN <= 512, "two accumulators must fit the 512 TMEM columns");
+    static_assert(PF >= 1 && PF <= NK && PF <= 4, "register prefetch depth");
+    static_assert(BN % 64 == 0, "N must be a multiple of 64");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* a_stage = smem_raw;
+    unsigned char* w_stage = a_stage + NSA * TC_A_STAGE;
+    float* stg_all = reinterpret_cast<float*>(w_stage + NWS * WBYTES);
+    float* extra = stg_all + TC_STG_BYTES / 4;  // two loader tables (ping-pong by tile)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(extra + 2 * AL::kExtra);
+    uint64_t* full_a = bars;                 // [NSA] count TCP_PROD
+    uint64_t* empty_a = full_a + NSA;        // [NSA] count 1 (tcgen05.commit)
+    uint64_t* full_w = empty_a + NSA;        // [NWS] count 1 + tx
+    uint64_t* empty_w = full_w + NWS;        // [NWS] count 1 (streamed only)
+    uint64_t* tmem_full = empty_w + NWS;     // [2] count 1
+    uint64_t* tmem_empty = tmem_full + 2;    // [2] count TCP_EPI
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* scratch = reinterpret_cast<float*>(tmem_slot + 4);  // 16 floats
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) tmem_alloc<(2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512)>(tmem_slot);
+    if (tid == 32) {
+        for (int s = 0; s < NSA; ++s) {
+            mbar_init(full_a + s, TCP_PROD);
+            mbar_init(empty_a + s, 1);
+        }
+        for (int s = 0; s < NWS; ++s) {
+            mbar_init(full_w + s, 1);
+            mbar_init(empty_w + s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tmem_full + s, 1);
+            mbar_init(tmem_empty + s, TCP_EPI);
+        }
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    constexpr uint32_t IDESC = umma_idesc_tf32(TC_BM, BN);
+
+    if (warp < 8) {
+        // ================================================================= epilogue
+        const int q = warp & 3, hlf = warp >> 2;
+        float* stg = stg_all + warp * (32 * TC_STG_LD);
+        const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1, row0 = tile * TC_BM;
+            ep.init(row0, M);
+            mbar_wait(tmem_full + acc, (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cb = 0; cb < BN / 64; ++cb) {
+                const int col0 = hlf * (BN / 2) + cb * 32;
+                // all global loads of this 32x32 block are issued first and stay in flight while the
+                // accumulator block is read from TMEM and transposed through shared memory
+                typename EP::Pre pre[8];
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    const int row = row0 + q * 32 + p * 4 + rsub;
+                    pre[p] = ep.load(row < M ? row : M - 1, col0 + c4);
+                }
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + col0) + 16 * hh, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<float4*>(stg + lane * TC_STG_LD + 16 * hh + 4 * i) =
+                            make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                }
+                __syncwarp();
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    const int r = p * 4 + rsub;
+                    const float4 x = *reinterpret_cast<const float4*>(stg + r * TC_STG_LD + c4);
+                    const int row = row0 + q * 32 + r;
+                    if (row < M) ep.store4(row, col0 + c4, x, pre[p]);
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            mbar_arrive_cta(tmem_empty + acc);  // this thread's TMEM reads of the accumulator are complete
+            ep.finish_group(scratch, tid, TCP_EPI, 1);
+        }
+    } else if (warp < 16) {
+        // ================================================================= A producers
+        const int ptid = tid - TCP_EPI;
+        const int kq = ptid & 7;
+        unsigned char* a_dst0 = a_stage + kq * TC_LBO_A + (ptid >> 3) * 16;
+        if constexpr (ASYNC) {
+            constexpr int D = NSA - 2;  // chunks in flight ahead of the transform
+            static_assert(!ASYNC || NSA >= 3, "async producers need >= 3 stages");
+            const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+            const int G = my_tiles * NK;
+            auto issue = [&](int g) {
+                if (g < G) {
+                    const int it = g / NK, kc = g - it * NK;
+                    const long long rbase = (long long)(blockIdx.x + it * gridDim.x) * TC_BM + (ptid >> 3);
+                    const int s = g % NSA;
+                    if (g >= NSA) mbar_wait(empty_a + s, ((g / NSA) - 1) & 1);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const long long row = rbase + 32 * i;
+                        const bool valid = row < M;
+                        cp_async16(a_dst0 + (size_t)s * TC_A_STAGE + i * (32 * 16), al.raw(valid ? row : 0, kc * TC_KC + kq * 4), valid);
+                    }
+                }
+                cp_async_commit();
+            };
+#pragma unroll
+            for (int g = 0; g < D; ++g) issue(g);
+            for (int g = 0; g < G; ++g) {
+                issue(g + D);
+                cp_async_wait<D>();  // this thread's pieces of chunk g have landed
+                const int it = g / NK, kc = g - it * NK;
+                const int row0 = (blockIdx.x + it * gridDim.x) * TC_BM;
+                if (kc == 0) {
+                    al.init_p(row0, M, extra + (it & 1) * AL::kExtra, ptid, TCP_PROD);
+                    if (AL::kExtra > 0) named_bar_sync(2, TCP_PROD);
+                }
+                const int s = g % NSA;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4* slot = reinterpret_cast<float4*>(a_dst0 + (size_t)s * TC_A_STAGE + i * (32 * 16));
+                    const int row = row0 + (ptid >> 3) + 32 * i;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row < M) v = al.xform(*slot, row, kc * TC_KC + kq * 4);
+                    v.x = tf32r(v.x);
+                    v.y = tf32r(v.y);
+                    v.z = tf32r(v.z);
+                    v.w = tf32r(v.w);
+                    *slot = v;
+                }
+                fence_proxy_async();
+                mbar_arrive_cta(full_a + s);
+            }
+            cp_async_wait<0>();
+        } else {
+        int it = 0, ga = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int row0 = tile * TC_BM;
+            al.init_p(row0, M, extra + (it & 1) * AL::kExtra, ptid, TCP_PROD);
+            if (AL::kExtra > 0) named_bar_sync(2, TCP_PROD);  // the tile's loader table is complete
+            float4 areg[PF][4];
+#pragma unroll
+            for (int c = 0; c < PF; ++c) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) areg[c][i] = al.load(i, c * TC_KC + kq * 4);
+            }
+#pragma unroll
+            for (int kc = 0; kc < NK; ++kc, ++ga) {
+                const int s = ga % NSA, use = ga / NSA;
+                if (use > 0) mbar_wait(empty_a + s, (use - 1) & 1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 v = areg[kc % PF][i];
+                    v.x = tf32r(v.x);
+                    v.y = tf32r(v.y);
+                    v.z = tf32r(v.z);
+                    v.w = tf32r(v.w);
+                    *reinterpret_cast<float4*>(a_dst0 + (size_t)s * TC_A_STAGE + i * (32 * 16)) = v;
+                }
+                if (kc + PF < NK) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) areg[kc % PF][i] = al.load(i, (kc + PF) * TC_KC + kq * 4);
+                }
+                fence_proxy_async();
+                mbar_arrive_cta(full_a + s);
+            }
+        }
+        }
+    } else if (warp == 16) {
+        // ================================================================= MMA issuer
+        if (lane == 0) {
+            int it = 0, ga = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                if (it >= 2) mbar_wait(tmem_empty + acc, ((it >> 1) - 1) & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int kc = 0; kc < NK; ++kc, ++ga) {
+                    const int s = ga % NSA;
+                    const int ws = WRES ? kc : ga % NSW;
+                    mbar_wait(full_w + ws, WRES ? 0 : (ga / NSW) & 1);
+                    mbar_wait(full_a + s, (ga / NSA) & 1);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(a_stage + (size_t)s * TC_A_STAGE);
+                    const uint32_t w_base = smem_u32(w_stage + (size_t)ws * WBYTES);
+#pragma unroll
+                    for (int k8 = 0; k8 < TC_KC / 8; ++k8) {
+                        const uint64_t da = umma_desc(a_base + 2 * k8 * TC_LBO_A, TC_LBO_A, 128);
+                        const uint64_t db = umma_desc(w_base + 2 * k8 * (BN * 16), BN * 16, 128);
+                        umma_tf32(tmem + acc * BN, da, db, IDESC, (kc > 0 || k8 > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_a + s);
+                    if (!WRES) umma_commit(empty_w + ws);
+                }
+                umma_commit(tmem_full + acc);
+            }
+        }
+    } else {
+        // ================================================================= weight loader
+        if (lane == 0) {
+            if (WRES) {
+                for (int c = 0; c < NK; ++c) {
+                    mbar_expect_tx(full_w + c, WBYTES);
+                    bulk_g2s(w_stage + (size_t)c * WBYTES, Wimg + (size_t)c * (BN * TC_KC), WBYTES, full_w + c);
+                }
+            } else {
+                int gw = 0;
+                for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                    for (int kc = 0; kc < NK; ++kc, ++gw) {
+                        const int ws = gw % NSW, use = gw / NSW;
+                        if (use > 0) mbar_wait(empty_w + ws, (use - 1) & 1);
+                        mbar_expect_tx(full_w + ws, WBYTES);
+                        bulk_g2s(w_stage + (size_t)ws * WBYTES, Wimg + (size_t)kc * (BN * TC_KC), WBYTES, full_w + ws);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<(2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512)>(tmem);
+}
+
+template <int BN, int KTOT, int NSA, int NSW, bool WRES, int PF, bool ASYNC, class AL, class EP>
+inline cudaError_t launch_gemm_tcp(const AL& al, const float* Wimg, const EP& ep, int M, cudaStream_t st) {
+    auto kern = gemm_tcp_kernel<BN, KTOT, NSA, NSW, WRES, PF, ASYNC, AL, EP>;
+    const int smem = tcp_smem_bytes<BN, KTOT, NSA, NSW, WRES>(AL::kExtra);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int ntiles = (M + TC_BM - 1) / TC_BM;
+    const int grid = ntiles < 148 ? ntiles : 148;
+    kern<<<grid, TCP_THREADS, smem, st>>>(al, Wimg, ep, M, ntiles);
+    return cudaGetLastError();
+}
+
+}  // namespace rtfs
