@@ -52,6 +52,18 @@ def make_inputs(batch, seed):
     return 0.1 * torch.randn(batch, L, generator=g), torch.rand(batch, 512, TV, generator=g)
 
 
+def measured_traffic(stage):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage's kernel at B=32 from the committed
+    ncu --set full capture (profiles/r01_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    v = d.get("stages", {}).get(stage)
+    return None if v is None else float(v["dram_bytes"])
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -63,17 +75,19 @@ def measured_peaks():
 
 # ------------------------------------------------------------------------------- algorithmic bytes
 def stage_bytes(B):
-    """Algorithmic HBM bytes per launch of each kernel stage (fp32).
+    """Algorithmic HBM bytes per launch of each kernel stage (fp32).  Stages as launched today:
+    DW_S2_POOL = one pass over gLN(d0) producing le0 (H), d1 (G) and the pool (G); DPRNN_FUSED = one dual-path RNN
+    (reads g [+ pool], writes g' [+ g]; average of the two paths); TFAR_GLOBAL = the 4-conv launch (5G) and le1 (2G).
     A = 4*256*T*F, H = 4*64*T*F, G = 4*64*Tc*Fc bytes per utterance."""
     T, Fq = L // 128 + 1, 129
     Tc, Fc = (T - 2) // 2 + 1, 64
     A, H, G = 4 * 256 * T * Fq * B, 4 * 64 * T * Fq * B, 4 * 64 * Tc * Fc * B
     return {
         "RTFS_SG_ENC_CONV": A, "RTFS_SG_BOTTLENECK": 2 * A, "RTFS_SG_GATE_PROJ": A + H, "RTFS_SG_DW_S1": 2 * H,
-        "RTFS_SG_DW_S2_POOL": H + 2 * G, "RTFS_SG_DPRNN_PREP": 3 * G, "RTFS_SG_DPRNN_GEMM0": 5 * G,
+        "RTFS_SG_DW_S2_POOL": 2 * H + 2 * G, "RTFS_SG_DPRNN_FUSED": 3 * G, "RTFS_SG_DPRNN_PREP": 3 * G, "RTFS_SG_DPRNN_GEMM0": 5 * G,
         "RTFS_SG_DPRNN_SCAN": 5 * G, "RTFS_SG_DPRNN_GEMML": 4 * G, "RTFS_SG_DPRNN_CONVT": 3 * G,
         "RTFS_SG_ATT_QKV": 2.5 * G, "RTFS_SG_ATT_CORE": 2.5 * G, "RTFS_SG_ATT_PROJ": 3 * G,
-        "RTFS_SG_TFAR_GLOBAL": 8 * G / 3, "RTFS_SG_TFAR_LE0": 2 * H, "RTFS_SG_TFAR_CAT_GLOBAL": 5 * G,
+        "RTFS_SG_TFAR_GLOBAL": 3.5 * G, "RTFS_SG_TFAR_LE0": 2 * H, "RTFS_SG_TFAR_CAT_GLOBAL": 5 * G,
         "RTFS_SG_TFAR_CAT_LOCAL": 2 * H + 2 * G, "RTFS_SG_RESID_OUT": 3 * A + 2 * H + 2 * G, "RTFS_SG_CAF_APPLY": 3 * A,
         "RTFS_SG_MASK": 3 * A, "RTFS_SG_DEC_GEMM": A * (1 + 18 / 256),
     }, (4 * A + 14 * H + 36 * G), ((6 + 4 * REPEATS) * A + 14 * REPEATS * H + 36 * REPEATS * G)
@@ -255,7 +269,7 @@ def run_gpu(args):
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": launches * K,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(top) if BATCH == 32 else None,
                      "peak_source": peak_src, "ms_per_launch": per_stage[top]["ms_per_launch"], "share_of_step": per_stage[top]["ms_per_step"] / stage_sum},
         "roofline_block": {"what": "RTFS block pass kernel chain, algorithmic 4A+14H+36G", "ms_per_pass": block_ms, "achieved": block_bytes / (block_ms * 1e-3) / 1e9,
                            "peak": peak, "unit": "GB/s", "frac": block_bytes / (block_ms * 1e-3) / 1e9 / peak},

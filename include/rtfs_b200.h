@@ -107,6 +107,7 @@ enum rtfs_stage {
     RTFS_SG_ATT_QKV, RTFS_SG_ATT_CORE, RTFS_SG_ATT_PROJ,
     RTFS_SG_TFAR_GLOBAL, RTFS_SG_TFAR_LE0, RTFS_SG_TFAR_CAT_GLOBAL, RTFS_SG_TFAR_CAT_LOCAL, RTFS_SG_RESID_OUT,
     RTFS_SG_CAF_VIDEO, RTFS_SG_CAF_APPLY, RTFS_SG_MASK, RTFS_SG_DEC_GEMM, RTFS_SG_DEC_ISTFT,
+    RTFS_SG_DPRNN_FUSED, /* one launch per dual-path RNN (dprnn_fused.cuh) instead of PREP..CONVT */
     RTFS_SG_COUNT
 };
 

@@ -47,6 +47,10 @@ bool use_persistent(int bit) {
     }();
     return (mask >> bit) & 1;
 }
+bool use_wide() {  // RTFS_NARROW_GEMM=1: 256-thread CTAs for gate+projection / residual conv (default 512: more loading warps)
+    static const bool v = !env_flag("RTFS_NARROW_GEMM");
+    return v;
+}
 bool use_unfold() {  // RTFS_NO_UNFOLD=1: overlapping-view GEMMs through the generic im2col-style loader
     static const bool v = !env_flag("RTFS_NO_UNFOLD");
     return v;
@@ -229,7 +233,7 @@ int run_bottleneck(const Ctx& c, const float* a0, float* a1, bool compute_stats)
     if (use_tc()) {
         StoreEpi4 ep{a1, 256, c.P[RTFS_P_BN_B]};
         if (use_persistent(0)) CK((launch_gemm_tcp<256, 256, 4, 3, false, 3, false>(al, c.P[RTFS_P_BN_WI], ep, (int)(d.B * d.P), c.st)));
-        else CK((launch_gemm_tc<256, 256, 3, 1, 4>(al, c.P[RTFS_P_BN_WI], ep, (int)(d.B * d.P), c.st)));
+        else CK((launch_gemm_tc<256, 256, 3, 1, 4, 256>(al, c.P[RTFS_P_BN_WI], ep, (int)(d.B * d.P), c.st)));
     } else {
         StoreEpi ep{a1, 256, c.P[RTFS_P_BN_B]};
         CK((launch_gemm<128, 256, false>(al, c.P[RTFS_P_BN_W], ep, (int)(d.B * d.P), 256, c.st)));
@@ -281,7 +285,7 @@ int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_f
             CKN(cudaMemset(a.dbg, 0, sizeof(long long) * 32 * tiles));
         }
         {
-            STAGE(RTFS_SG_DPRNN_GEMM0);
+            STAGE(RTFS_SG_DPRNN_FUSED);
             CK(launch_dprnn_fused(a, c.st));
         }
         if (dbg) {  // phase timeline of a few tiles (cycles between the stamps of dprnn_fused.cuh)
@@ -336,7 +340,7 @@ int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_f
             if (use_tc()) {
                 StoreEpi4 ep{U, 256, nullptr};
                 if (use_unfold()) CK((launch_gemm_tc_unfold<256, 3, 1>(n, c.P[basei + 0], ep, M, c.st)));
-                else CK((launch_gemm_tc<256, 512, 3, 1, 2>(al, c.P[basei + 0], ep, M, c.st)));
+                else CK((launch_gemm_tc<256, 512, 3, 1, 2, 256>(al, c.P[basei + 0], ep, M, c.st)));
             } else {
                 StoreEpi ep{U, 256, nullptr};
                 CK((launch_gemm<128, 512, false>(al, c.P[base + 2], ep, M, 256, c.st)));
@@ -355,7 +359,7 @@ int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_f
             STAGE(RTFS_SG_DPRNN_GEMML);
             if (use_tc()) {
                 StoreEpi4 ep{U, 192, nullptr};
-                CK((launch_gemm_tc<192, 64, 2, 2, 2>(al, c.P[basei + l], ep, M, c.st)));
+                CK((launch_gemm_tc<192, 64, 2, 2, 2, 256>(al, c.P[basei + l], ep, M, c.st)));
             } else {
                 StoreEpi ep{U, 192, nullptr};
                 CK((launch_gemm<64, 64, false>(al, c.P[pw], ep, M, 192, c.st)));
@@ -376,7 +380,7 @@ int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_f
         if (use_tc()) {
             ConvTEpi4 ep{g_out, resid, c.P[base + 15], S, n_other, which, d.Tc, d.Fc};
             if (use_unfold()) CK((launch_gemm_tc_unfold<64, 4, 2>(hpad, c.P[basei + 4], ep, nseq * (S + 7), c.st)));
-            else CK((launch_gemm_tc<64, 512, 4, 2, 2>(al, c.P[basei + 4], ep, nseq * (S + 7), c.st)));
+            else CK((launch_gemm_tc<64, 512, 4, 2, 2, 256>(al, c.P[basei + 4], ep, nseq * (S + 7), c.st)));
         } else {
             ConvTEpi ep{g_out, resid, c.P[base + 15], S, n_other, which, d.Tc, d.Fc};
             CK((launch_gemm<64, 512, false>(al, c.P[base + 14], ep, nseq * (S + 7), 64, c.st)));
@@ -481,7 +485,7 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out) {
         if (use_tc()) {
             StatsEpi4 ep{p_pre, 64, P[RTFS_P_PJ_B], c.stat(RTFS_ST_PJ), (int)d.P, d.B};
             if (use_persistent(1)) CK((launch_gemm_tcp<64, 256, 7, 1, true, 2, true>(al, P[RTFS_P_PJ_WI], ep, M, c.st)));
-            else CK((launch_gemm_tc<64, 256, 4, 2, 2>(al, P[RTFS_P_PJ_WI], ep, M, c.st)));
+                        else CK((launch_gemm_tc<64, 256, 4, 2, 2, 256>(al, P[RTFS_P_PJ_WI], ep, M, c.st)));
         } else {
             StatsEpi ep{p_pre, 64, P[RTFS_P_PJ_B], c.stat(RTFS_ST_PJ), (int)d.P, d.B};
             CK((launch_gemm<64, 256, false>(al, P[RTFS_P_PJ_W], ep, M, 64, c.st)));
@@ -636,7 +640,8 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out) {
         if (use_tc()) {
             ResidOutEpi4 ep{out, P[RTFS_P_RC_B], x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], addend, 0.f};
             if (use_persistent(2)) CK((launch_gemm_tcp<256, 64, 4, 1, true, 2, false>(al, P[RTFS_P_RC_WI], ep, M, c.st)));
-            else CK((launch_gemm_tc<256, 64, 2, 2, 2>(al, P[RTFS_P_RC_WI], ep, M, c.st)));
+            else if (use_wide()) CK((launch_gemm_tc<256, 64, 2, 2, 2, 512>(al, P[RTFS_P_RC_WI], ep, M, c.st)));
+            else CK((launch_gemm_tc<256, 64, 2, 2, 2, 256>(al, P[RTFS_P_RC_WI], ep, M, c.st)));
         } else {
             ResidOutEpi ep{out, P[RTFS_P_RC_B], x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], addend, 0.f};
             CK((launch_gemm<128, 64, false>(al, P[RTFS_P_RC_W], ep, M, 256, c.st)));
@@ -680,7 +685,7 @@ int run_mask(const Ctx& c, const float* refined, const float* a0, float* z) {
     if (use_tc()) {
         MaskEpi4 ep{z, c.P[RTFS_P_MK_B], a0};
         if (use_persistent(3)) CK((launch_gemm_tcp<256, 256, 4, 3, false, 3, false>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
-        else CK((launch_gemm_tc<256, 256, 3, 1, 4>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
+        else CK((launch_gemm_tc<256, 256, 3, 1, 4, 256>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
     } else {
         MaskEpi ep{z, c.P[RTFS_P_MK_B], a0};
         CK((launch_gemm<128, 256, false>(al, c.P[RTFS_P_MK_W], ep, (int)(d.B * d.P), 256, c.st)));

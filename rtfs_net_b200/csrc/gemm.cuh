@@ -48,13 +48,14 @@ struct PlainLoader {
     long long lda;
     int K;  // real K (columns >= K read as zero)
     static constexpr int kExtra = 0;
-    int row0_, M_;
+    int row0_, M_, rs_;
     DEVINL void init(int row0, int M, float*) {
         row0_ = row0 + (threadIdx.x >> 3);
+        rs_ = blockDim.x >> 3;
         M_ = M;
     }
     DEVINL float4 load(int i, int k) const {
-        const int row = row0_ + 32 * i;
+        const int row = row0_ + rs_ * i;
         if (row < M_ && k < K) return ldg4(A + (long long)row * lda + k);
         return make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -67,7 +68,7 @@ struct GlnActLoader {
     GlnRef gln;
     int P, B;  // rows per sample, samples
     static constexpr int kExtra = 4 * C;
-    int row0_, M_, bfirst_, split_;
+    int row0_, M_, rs_, bfirst_, split_;
     const float* tab_;
     DEVINL void init(int row0, int M, float* extra) {
         bfirst_ = row0 / P;
@@ -75,6 +76,7 @@ struct GlnActLoader {
         fill_gln_table(extra, gln, bfirst_, B, C);
         tab_ = extra;
         row0_ = row0 + (threadIdx.x >> 3);
+        rs_ = blockDim.x >> 3;
         M_ = M;
     }
     // producer-group variant (persistent kernel): ptid in [0, nthr)
@@ -84,10 +86,11 @@ struct GlnActLoader {
         fill_gln_table(extra, gln, bfirst_, B, C, ptid, nthr);
         tab_ = extra;
         row0_ = row0 + (ptid >> 3);
+        rs_ = nthr >> 3;
         M_ = M;
     }
     DEVINL float4 load(int i, int k) const {
-        const int row = row0_ + 32 * i;
+        const int row = row0_ + rs_ * i;
         if (row >= M_) return make_float4(0.f, 0.f, 0.f, 0.f);
         return xform(ldg4(A + (long long)row * C + k), row, k);
     }
@@ -121,20 +124,22 @@ struct GateLoader {
     const float* slope;  // 1 float
     int C;
     static constexpr int kExtra = 0;
-    int row0_, M_;
+    int row0_, M_, rs_;
     float a_;
     DEVINL void init(int row0, int M, float*) {
         row0_ = row0 + (threadIdx.x >> 3);
+        rs_ = blockDim.x >> 3;
         M_ = M;
         a_ = __ldg(slope);
     }
-    DEVINL void init_p(int row0, int M, float*, int ptid, int) {
+    DEVINL void init_p(int row0, int M, float*, int ptid, int nthr) {
         row0_ = row0 + (ptid >> 3);
+        rs_ = nthr >> 3;
         M_ = M;
         a_ = __ldg(slope);
     }
     DEVINL float4 load(int i, int k) const {
-        const int row = row0_ + 32 * i;
+        const int row = row0_ + rs_ * i;
         if (row >= M_) return make_float4(0.f, 0.f, 0.f, 0.f);
         return xform(ldg4(A + (long long)row * C + k), row, k);
     }
@@ -156,20 +161,22 @@ struct PreluLoader {
     const float* slope;
     int C;
     static constexpr int kExtra = 0;
-    int row0_, M_;
+    int row0_, M_, rs_;
     float a_;
     DEVINL void init(int row0, int M, float*) {
         row0_ = row0 + (threadIdx.x >> 3);
+        rs_ = blockDim.x >> 3;
         M_ = M;
         a_ = __ldg(slope);
     }
-    DEVINL void init_p(int row0, int M, float*, int ptid, int) {
+    DEVINL void init_p(int row0, int M, float*, int ptid, int nthr) {
         row0_ = row0 + (ptid >> 3);
+        rs_ = nthr >> 3;
         M_ = M;
         a_ = __ldg(slope);
     }
     DEVINL float4 load(int i, int k) const {
-        const int row = row0_ + 32 * i;
+        const int row = row0_ + rs_ * i;
         if (row >= M_) return make_float4(0.f, 0.f, 0.f, 0.f);
         return xform(ldg4(A + (long long)row * C + k), row, k);
     }
@@ -194,7 +201,7 @@ struct TfarLoader {
     GlnRef n_l, n_d, n_g, n_e;
     int T, F, Tc, Fc, B;
     static constexpr int kExtra = 4 * 4 * 64;  // 4 norms x [2][64][2]
-    int row0_, M_, bfirst_, P_;
+    int row0_, M_, rs_, bfirst_, P_;
     const float* tab_;
     long long offc_[4];
     int s_[4];
@@ -208,10 +215,11 @@ struct TfarLoader {
         fill_gln_table(extra + 768, n_e, bfirst_, B, 64, ptid, nthr);
         tab_ = extra;
         row0_ = row0 + (ptid >> 3);
+        rs_ = nthr >> 3;
         M_ = M;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            int row = row0_ + 32 * i;
+            int row = row0_ + rs_ * i;
             if (row >= M) row = M - 1;
             const int b = row / P_;
             const int p = row - b * P_;
@@ -226,7 +234,7 @@ struct TfarLoader {
         return fmaf(x, tb[0], tb[1]);
     }
     DEVINL float4 load(int i, int k) const {
-        const int row = row0_ + 32 * i;
+        const int row = row0_ + rs_ * i;
         if (row >= M_) return make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 xl = ldg4(lec + (long long)row * 64 + k);
         const float4 xd = ldg4(d0 + (long long)row * 64 + k);
@@ -248,9 +256,10 @@ struct Im2colLoader {
     const float* spec;  // [B][T][F][2]
     int T, F;
     static constexpr int kExtra = 0;
-    int row0_, M_;
+    int row0_, M_, rs_;
     DEVINL void init(int row0, int M, float*) {
         row0_ = row0 + (threadIdx.x >> 3);
+        rs_ = blockDim.x >> 3;
         M_ = M;
     }
     DEVINL float2 tap(int b, int t, int f, int tapi) const {
@@ -260,7 +269,7 @@ struct Im2colLoader {
         return ldg2(spec + (((long long)b * T + tt) * F + ff) * 2);
     }
     DEVINL float4 load(int i, int k) const {
-        const int row = row0_ + 32 * i;
+        const int row = row0_ + rs_ * i;
         if (row >= M_ || k >= 18) return make_float4(0.f, 0.f, 0.f, 0.f);
         const int P = T * F;
         const int b = row / P, p = row - b * P;

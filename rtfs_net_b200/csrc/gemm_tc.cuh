@@ -308,13 +308,15 @@ template <int BN, int NS>
 __host__ __device__ constexpr int tc_stage_bytes() {
     return NS * (TC_A_STAGE + BN * 128);
 }
-template <int BN, int NS>
+template <int BN, int NS, int NT = 256>
 __host__ __device__ constexpr int tc_smem_bytes(int extra_floats) {
-    return (tc_stage_bytes<BN, NS>() > TC_STG_BYTES ? tc_stage_bytes<BN, NS>() : TC_STG_BYTES) + extra_floats * 4 + 256 + 128;
+    return (tc_stage_bytes<BN, NS>() > (NT / 32) * 32 * TC_STG_LD * 4 ? tc_stage_bytes<BN, NS>() : (NT / 32) * 32 * TC_STG_LD * 4) + extra_floats * 4 + 256 + 128;
 }
 
-template <int BN, int KTOT, int NS, int MINB, int PF, class AL, class EP>
-__global__ void __launch_bounds__(TC_THREADS, MINB) gemm_tc_kernel(AL al, const float* __restrict__ Wimg, EP ep, int M) {
+// NT = 256 or 512 threads: HBM bandwidth on this part scales with the number of warps that issue loads
+// (tools/probe/inflight_probe2.cu: 8 warps/SM ~4 TB/s, 16 ~5.9, 32 ~6.1), so the stream-heavy instances run 2 x 512.
+template <int BN, int KTOT, int NS, int MINB, int PF, int NT, class AL, class EP>
+__global__ void __launch_bounds__(NT, MINB) gemm_tc_kernel(AL al, const float* __restrict__ Wimg, EP ep, int M) {
     constexpr int NK = KTOT / TC_KC;
     static_assert(PF >= 1 && PF <= 4, "A-operand register prefetch depth (chunks in flight per thread)");
     constexpr int WBYTES = BN * 128;
@@ -323,7 +325,11 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) gemm_tc_kernel(AL al, const 
     static_assert(KTOT % TC_KC == 0, "K must be a multiple of 32");
     static_assert(BN % 64 == 0 && BN <= 256, "N must be 64, 128, 192 or 256");
     static_assert(NK <= NS || NS >= 3, "a ring shorter than K needs >= 3 stages");
-    constexpr int STAGE_AREA = tc_stage_bytes<BN, NS>() > TC_STG_BYTES ? tc_stage_bytes<BN, NS>() : TC_STG_BYTES;
+    constexpr int RPT = 1024 / NT;          // A rows per thread per chunk (4 or 2)
+    constexpr int RS = NT / 8;              // row stride between them
+    constexpr int STG_BYTES = (NT / 32) * 32 * TC_STG_LD * 4;
+    static_assert(NT == 256 || NT == 512, "256 or 512 threads");
+    constexpr int STAGE_AREA = tc_stage_bytes<BN, NS>() > STG_BYTES ? tc_stage_bytes<BN, NS>() : STG_BYTES;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* a_stage = smem_raw;
@@ -369,11 +375,11 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) gemm_tc_kernel(AL al, const 
     unsigned char* a_dst0 = a_stage + kq * TC_LBO_A + (tid >> 3) * 16;
     constexpr uint32_t IDESC = umma_idesc_tf32(TC_BM, BN);
 
-    float4 areg[PF][4];
+    float4 areg[PF][RPT];
 #pragma unroll
     for (int c = 0; c < PF && c < NK; ++c) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) areg[c][i] = al.load(i, c * TC_KC + kq * 4);
+        for (int i = 0; i < RPT; ++i) areg[c][i] = al.load(i, c * TC_KC + kq * 4);
     }
 
 #pragma unroll
@@ -386,17 +392,17 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) gemm_tc_kernel(AL al, const 
             issue_w(c);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < RPT; ++i) {
             float4 v = areg[kc % PF][i];
             v.x = tf32r(v.x);
             v.y = tf32r(v.y);
             v.z = tf32r(v.z);
             v.w = tf32r(v.w);
-            *reinterpret_cast<float4*>(a_dst0 + (size_t)s * TC_A_STAGE + i * (32 * 16)) = v;
+            *reinterpret_cast<float4*>(a_dst0 + (size_t)s * TC_A_STAGE + i * (RS * 16)) = v;
         }
         if (kc + PF < NK) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) areg[kc % PF][i] = al.load(i, (kc + PF) * TC_KC + kq * 4);
+            for (int i = 0; i < RPT; ++i) areg[kc % PF][i] = al.load(i, (kc + PF) * TC_KC + kq * 4);
         }
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
         __syncthreads();
@@ -420,12 +426,13 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) gemm_tc_kernel(AL al, const 
 
     // ---- epilogue: warp w reads TMEM lanes 32*(w&3).. (rows), column half (w>>2)
     {
+        constexpr int NCG = (NT / 128) < (BN / 32) ? (NT / 128) : (BN / 32);  // column groups sharing a lane quarter
         const int q = warp & 3, hlf = warp >> 2;
         float* stg = reinterpret_cast<float*>(smem_raw) + warp * (32 * TC_STG_LD);
         const int rsub = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll 1
-        for (int cb = 0; cb < BN / 64; ++cb) {
-            const int col0 = hlf * (BN / 2) + cb * 32;
+        for (int cb = 0; cb < (hlf < NCG ? BN / (32 * NCG) : 0); ++cb) {
+            const int col0 = hlf * (BN / NCG) + cb * 32;
             // all global loads of this 32x32 block are issued first and stay in flight while the
             // accumulator block is read from TMEM and transposed through shared memory
             typename EP::Pre pre[8];
@@ -609,17 +616,17 @@ inline cudaError_t launch_gemm_tc_unfold(const float* X, const float* Wimg, cons
     return cudaGetLastError();
 }
 
-template <int BN, int KTOT, int NS, int MINB, int PF, class AL, class EP>
+template <int BN, int KTOT, int NS, int MINB, int PF, int NT, class AL, class EP>
 inline cudaError_t launch_gemm_tc(const AL& al, const float* Wimg, const EP& ep, int M, cudaStream_t st) {
-    auto kern = gemm_tc_kernel<BN, KTOT, NS, MINB, PF, AL, EP>;
-    const int smem = tc_smem_bytes<BN, NS>(AL::kExtra);
+    auto kern = gemm_tc_kernel<BN, KTOT, NS, MINB, PF, NT, AL, EP>;
+    const int smem = tc_smem_bytes<BN, NS, NT>(AL::kExtra);
     static bool configured = false;  // one flag per instantiation
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<(M + TC_BM - 1) / TC_BM, TC_THREADS, smem, st>>>(al, Wimg, ep, M);
+    kern<<<(M + TC_BM - 1) / TC_BM, NT, smem, st>>>(al, Wimg, ep, M);
     return cudaGetLastError();
 }
 
