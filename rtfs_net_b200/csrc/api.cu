@@ -465,7 +465,9 @@ int run_mhsa(const Ctx& c, const float* g_in, float* g_out) {
     return 0;
 }
 
-int run_block(const Ctx& c, const float* x, const float* addend, float* out) {
+// caf_fused: apply the CAF fusion (vk/att already produced by caf_video_kernel) to the block output in the
+// residual-conv epilogue; addend is then added after the fusion (refinement_module.py:50-56).
+int run_block(const Ctx& c, const float* x, const float* addend, float* out, bool caf_fused = false) {
     const Dims& d = c.d;
     const float* const* P = c.P;
     const int M = (int)(d.B * d.P);
@@ -637,7 +639,12 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out) {
         al.Fc = d.Fc;
         al.B = d.B;
         STAGE(RTFS_SG_RESID_OUT);
-        if (use_tc()) {
+        if (caf_fused) {
+            ResidOutCafEpi4 ep{out, P[RTFS_P_RC_B], x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], addend,
+                               c.buf(RTFS_WS_VK), c.buf(RTFS_WS_ATT), P[RTFS_P_CAF_SK], P[RTFS_P_CAF_TK], P[RTFS_P_CAF_SV], P[RTFS_P_CAF_TV],
+                               d.T, d.F, d.Tv, 0.f};
+            CK((launch_gemm_tc<256, 64, 2, 2, 2, 512>(al, P[RTFS_P_RC_WI], ep, M, c.st)));
+        } else if (use_tc()) {
             ResidOutEpi4 ep{out, P[RTFS_P_RC_B], x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], addend, 0.f};
             if (use_persistent(2)) CK((launch_gemm_tcp<256, 64, 4, 1, true, 2, false>(al, P[RTFS_P_RC_WI], ep, M, c.st)));
             else if (use_wide()) CK((launch_gemm_tc<256, 64, 2, 2, 2, 512>(al, P[RTFS_P_RC_WI], ep, M, c.st)));
@@ -650,7 +657,23 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out) {
     return 0;
 }
 
+int run_caf_video(const Ctx& c, const float* video);
+
 int run_caf(const Ctx& c, const float* audio, const float* video, const float* addend, float* out) {
+    const Dims& d = c.d;
+    const float* const* P = c.P;
+    RUN(run_caf_video(c, video));
+    CafApplyArgs aa{audio, addend, c.buf(RTFS_WS_VK), c.buf(RTFS_WS_ATT), P[RTFS_P_CAF_SK], P[RTFS_P_CAF_TK],
+                    P[RTFS_P_CAF_SV], P[RTFS_P_CAF_TV], out, d.T, d.F, 256, d.Tv, d.B * d.P * 64};
+    long long blocks = (aa.total4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    STAGE(RTFS_SG_CAF_APPLY);
+    caf_apply_kernel<<<(unsigned)blocks, 256, 0, c.st>>>(aa);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int run_caf_video(const Ctx& c, const float* video) {
     const Dims& d = c.d;
     const float* const* P = c.P;
     CafVideoArgs va{video, P[RTFS_P_CAF_WR], P[RTFS_P_CAF_BR], P[RTFS_P_CAF_GR], P[RTFS_P_CAF_BER],
@@ -663,17 +686,8 @@ int run_caf(const Ctx& c, const float* audio, const float* video, const float* a
         CKN(cudaFuncSetAttribute(caf_video_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         cfg_smem = smem;
     }
-    {
-        STAGE(RTFS_SG_CAF_VIDEO);
-        caf_video_kernel<<<d.B, 256, smem, c.st>>>(va);
-        CK(cudaGetLastError());
-    }
-    CafApplyArgs aa{audio, addend, c.buf(RTFS_WS_VK), c.buf(RTFS_WS_ATT), P[RTFS_P_CAF_SK], P[RTFS_P_CAF_TK],
-                    P[RTFS_P_CAF_SV], P[RTFS_P_CAF_TV], out, d.T, d.F, 256, d.Tv, d.B * d.P * 64};
-    long long blocks = (aa.total4 + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    STAGE(RTFS_SG_CAF_APPLY);
-    caf_apply_kernel<<<(unsigned)blocks, 256, 0, c.st>>>(aa);
+    STAGE(RTFS_SG_CAF_VIDEO);
+    caf_video_kernel<<<d.B, 256, smem, c.st>>>(va);
     CK(cudaGetLastError());
     return 0;
 }
@@ -825,9 +839,14 @@ int rtfs_avnet_forward(const float* const* params, const float* wav, const float
     RUN(run_encoder(c, wav, a0, L));
     RUN(run_bottleneck(c, a0, a1, false));
     // refinement_module.py:45-62 with fusion_repeats = 1
-    RUN(run_block(c, a1, nullptr, xa));
-    RUN(run_caf(c, xa, video, repeats > 1 ? a1 : nullptr, xb));
     float *cur = xb, *other = xa;
+    if (use_tc() && !env_flag("RTFS_UNFUSED_CAF")) {
+        RUN(run_caf_video(c, video));
+        RUN(run_block(c, a1, repeats > 1 ? a1 : nullptr, xb, true));
+    } else {
+        RUN(run_block(c, a1, nullptr, xa));
+        RUN(run_caf(c, xa, video, repeats > 1 ? a1 : nullptr, xb));
+    }
     for (int i = 1; i < repeats; ++i) {
         RUN(run_block(c, cur, (i + 1 < repeats) ? a1 : nullptr, other));
         float* t = cur;

@@ -230,6 +230,59 @@ struct ResidOutEpi4 {
     DEVINL void finish_group(float*, int, int, int) {}
 };
 
+// residual_conv epilogue of the FIRST block pass with the CAF fusion (layers/fusion.py:252-274) applied to the block
+// output in registers: y = ReLU(v*sk+tk) * vk[b][near(t)][c] + att[b][near(t)][c] * (v*sv+tv) [+ a1], v = block output.
+// Saves the separate streaming pass over the (B,T,F,256) tensor (one read + one write).
+struct ResidOutCafEpi4 {
+    float* out;
+    const float* bias;
+    const float* x;
+    const float* wg;
+    const float* bg;
+    const float* slope;
+    const float* a1;  // may be null
+    const float* vk;  // (B,Tv,256)
+    const float* att;
+    const float* sk;
+    const float* tk;
+    const float* sv;
+    const float* tv;
+    int T, F, Tv;
+    float a_;
+    struct Pre {
+        float4 x, a1;
+    };
+    DEVINL void init(int, int) { a_ = __ldg(slope); }
+    DEVINL Pre load(int row, int col) const {
+        const long long o = (long long)row * 256 + col;
+        Pre p;
+        p.x = ldg4(x + o);
+        p.a1 = a1 ? ldg4(a1 + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+        return p;
+    }
+    DEVINL void store4(int row, int col, float4 v, const Pre& p) {
+        const long long o = (long long)row * 256 + col;
+        const float4 w = ldg4(wg + col), b = ldg4(bg + col), bi = ldg4(bias + col);
+        v.x += bi.x + prelu(fmaf(w.x, p.x.x, b.x), a_);
+        v.y += bi.y + prelu(fmaf(w.y, p.x.y, b.y), a_);
+        v.z += bi.z + prelu(fmaf(w.z, p.x.z, b.z), a_);
+        v.w += bi.w + prelu(fmaf(w.w, p.x.w, b.w), a_);
+        const int bt = row / F, t = bt % T, bb = bt / T;
+        const int tvi = (t * Tv) / T;  // nearest: floor(t * Tv / T) (< Tv)
+        const long long vo = ((long long)bb * Tv + tvi) * 256 + col;
+        const float4 k = ldg4(vk + vo), at = ldg4(att + vo);
+        const float4 s1 = ldg4(sk + col), t1 = ldg4(tk + col), s2 = ldg4(sv + col), t2 = ldg4(tv + col);
+        float4 y;
+        y.x = fmaxf(fmaf(v.x, s1.x, t1.x), 0.f) * k.x + at.x * fmaf(v.x, s2.x, t2.x) + p.a1.x;
+        y.y = fmaxf(fmaf(v.y, s1.y, t1.y), 0.f) * k.y + at.y * fmaf(v.y, s2.y, t2.y) + p.a1.y;
+        y.z = fmaxf(fmaf(v.z, s1.z, t1.z), 0.f) * k.z + at.z * fmaf(v.z, s2.z, t2.z) + p.a1.z;
+        y.w = fmaxf(fmaf(v.w, s1.w, t1.w), 0.f) * k.w + at.w * fmaf(v.w, s2.w, t2.w) + p.a1.w;
+        *reinterpret_cast<float4*>(out + o) = y;
+    }
+    DEVINL void finish(float*) {}
+    DEVINL void finish_group(float*, int, int, int) {}
+};
+
 // S^3 mask epilogue (mask_generator.py:67-99); GEMM columns interleaved on the host: col 2c = real-half
 // channel c, col 2c+1 = imag-half channel c+128 -> a float4 holds (re c, im c, re c+1, im c+1).
 struct MaskEpi4 {
