@@ -579,7 +579,7 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out, boo
             a.Ti = d.T; a.Fi = d.F;
             a.w[0] = P[RTFS_P_C0_LW]; a.out[0] = lec; a.sums[0] = c.stat(RTFS_ST_C0L);
             STAGE(RTFS_SG_TFAR_CAT_LOCAL);
-            CK((launch_dwroll<XrTfar, 1, false, 288>(xf, a, d.B, c.st)));
+            CK((launch_dwroll<XrTfar, 1, false, 288, false>(xf, a, d.B, c.st)));
         }
     } else {
         // S10-S12 TF-AR units                                                  tdanet.py:124-129, layers/fusion.py:54-69

@@ -20,6 +20,7 @@
 //   * the transposed conv runs with positions on the lanes, so its epilogue (bias + residual + store) is the
 //     coalesced transposed-through-shared-memory store of gemm_tc.cuh.
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
@@ -75,11 +76,42 @@ DEVINL float df_rcp(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// one step of c_t = f_t c_{t-1} + (1 - f_t) u0_t, f_t = sigmoid(u1_t + v_f c_{t-1} + b_f); vf and u1 are pre-scaled by -log2(e)
-template <bool PRED>
+DEVINL float df_tanh(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// Gate arithmetic of the recurrences (template parameter GATE of the kernel):
+//   0: sigmoid(x) = 1 / (1 + 2^(-x log2 e))   MUFU.EX2 + MUFU.RCP (2 quarter-rate ops per gate)
+//   1: sigmoid(x) = 0.5 + 0.5 tanh(x/2)       one MUFU.TANH (max rel. error 2^-11 on tanh)
+//   2: as 0 with the reciprocal done by a bit-trick seed + 3 Newton steps on the FMA pipe (1 MUFU per gate)
+template <int GATE>
+DEVINL constexpr float df_prescale() { return GATE == 1 ? 0.5f : DF_NL2E; }
+DEVINL float df_rcp_newton(float d) {  // d in [1, inf): 1/d to ~1e-7 relative
+    float r = __uint_as_float(0x7EF311C3u - __float_as_uint(d));
+    r = r * fmaf(-d, r, 2.f);
+    r = r * fmaf(-d, r, 2.f);
+    r = r * fmaf(-d, r, 2.f);
+    return r;
+}
+template <int GATE>
+DEVINL float df_gate(float t) {  // t = pre-scaled pre-activation
+    if (GATE == 1) return fmaf(0.5f, df_tanh(t), 0.5f);
+    const float d = 1.f + df_ex2(t);
+    if (GATE == 2) return d < 1e30f ? df_rcp_newton(d) : 0.f;
+    return df_rcp(d);
+}
+// one step of c_t = f_t c_{t-1} + (1 - f_t) u0_t, f_t = sigmoid(u1_t + v_f c_{t-1} + b_f); vf and u1 are pre-scaled
+template <bool PRED, int GATE>
 DEVINL float df_cstep(float c, float vf, float u1, float u0, float* dst, bool valid) {
-    const float f = df_rcp(1.f + df_ex2(fmaf(vf, c, u1)));
-    const float cn = fmaf(f, c - u0, u0);
+    float cn;
+    if (GATE == 1) {  // c_t = A + tanh(.) * B with A = (c + u0)/2, B = (c - u0)/2 formed beside the MUFU op
+        const float th = df_tanh(fmaf(vf, c, u1));
+        cn = fmaf(th, 0.5f * (c - u0), 0.5f * (c + u0));
+    } else {
+        const float f = df_gate<GATE>(fmaf(vf, c, u1));
+        cn = fmaf(f, c - u0, u0);
+    }
     if (PRED) {
         if (valid) *dst = cn;
         return valid ? cn : c;
@@ -91,7 +123,7 @@ DEVINL float df_cstep(float c, float vf, float u1, float u0, float* dst, bool va
 // h_t = r_t c_t + (1 - r_t) x'_t, r_t = sigmoid(u2_t + v_r c_{t-1} + b_r) for the 16 steps of TMEM column block m.
 // FULL: all 16 steps lie inside [p_lo, p_hi) (no per-step predicates); K4: x' = highway projection (acc1), else the
 // previous layer's h read in place from the slab.  rev: scan order is descending (c_{t-1} is the row above).
-template <bool FULL, bool K4>
+template <bool FULL, bool K4, int GATE>
 DEVINL void df_hchunk(uint32_t tl, int m, bool rev, int p_lo, int p_hi, int p_end, float vr, float br, const float* csj, unsigned char* hb) {
     uint32_t ua[16], ub[16];
     tmem_ld16(tl + 16 * m, ua);
@@ -114,7 +146,7 @@ DEVINL void df_hchunk(uint32_t tl, int m, bool rev, int p_lo, int p_hi, int p_en
     for (int i = 0; i < 16; ++i) {
         const float x = K4 ? __uint_as_float(ub[i]) : xp[i];
         const float cprev = rev ? cc[i + 2] : cc[i];
-        const float r = df_rcp(1.f + df_ex2(fmaf(vr, cprev, (__uint_as_float(ua[i]) + br) * DF_NL2E)));
+        const float r = df_gate<GATE>(fmaf(vr, cprev, (__uint_as_float(ua[i]) + br) * df_prescale<GATE>()));
         hv[i] = tf32r(fmaf(r, cc[i + 1] - x, x));
     }
 #pragma unroll
@@ -125,6 +157,7 @@ DEVINL void df_hchunk(uint32_t tl, int m, bool rev, int p_lo, int p_hi, int p_en
     }
 }
 
+template <int GATE>
 __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* hbuf = smem_raw;
@@ -311,7 +344,7 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
         // ---- c-recurrence: warps q = 0 (forward columns 0-31) and q = 1 (backward columns 32-63)
         if (q < 2 && seq_on) {
             const int j = q * 32 + lane;
-            const float vf = __ldg(a.wc[ly] + j) * DF_NL2E, bf = __ldg(a.bias[ly] + j);
+            const float vf = __ldg(a.wc[ly] + j) * df_prescale<GATE>(), bf = __ldg(a.bias[ly] + j);
             const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
             float c = 0.f;
             float* csj = cs + j;
@@ -324,25 +357,25 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
                 tmem_ld_wait();
                 float u1[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) u1[i] = (__uint_as_float(ub[i]) + bf) * DF_NL2E;  // off the serial chain
+                for (int i = 0; i < 16; ++i) u1[i] = (__uint_as_float(ub[i]) + bf) * df_prescale<GATE>();  // off the serial chain
                 const bool full = 16 * m >= p_lo && 16 * m + 16 <= p_hi;
                 if (q == 0) {
                     if (full) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) c = df_cstep<false>(c, vf, u1[i], __uint_as_float(ua[i]), csj + (16 * m + i) * 64, true);
+                        for (int i = 0; i < 16; ++i) c = df_cstep<false, GATE>(c, vf, u1[i], __uint_as_float(ua[i]), csj + (16 * m + i) * 64, true);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
-                            c = df_cstep<true>(c, vf, u1[i], __uint_as_float(ua[i]), csj + (16 * m + i) * 64, 16 * m + i >= p_lo && 16 * m + i < p_hi);
+                            c = df_cstep<true, GATE>(c, vf, u1[i], __uint_as_float(ua[i]), csj + (16 * m + i) * 64, 16 * m + i >= p_lo && 16 * m + i < p_hi);
                     }
                 } else {
                     if (full) {
 #pragma unroll
-                        for (int i = 15; i >= 0; --i) c = df_cstep<false>(c, vf, u1[i], __uint_as_float(ua[i]), csj + (16 * m + i) * 64, true);
+                        for (int i = 15; i >= 0; --i) c = df_cstep<false, GATE>(c, vf, u1[i], __uint_as_float(ua[i]), csj + (16 * m + i) * 64, true);
                     } else {
 #pragma unroll
                         for (int i = 15; i >= 0; --i)
-                            c = df_cstep<true>(c, vf, u1[i], __uint_as_float(ua[i]), csj + (16 * m + i) * 64, 16 * m + i >= p_lo && 16 * m + i < p_hi);
+                            c = df_cstep<true, GATE>(c, vf, u1[i], __uint_as_float(ua[i]), csj + (16 * m + i) * 64, 16 * m + i >= p_lo && 16 * m + i < p_hi);
                     }
                 }
                 __syncwarp();
@@ -355,7 +388,7 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
         if (a.dbg != nullptr && tid == 64) a.dbg[(gridDim.x + blockIdx.x) * 16 + 2 * ly] = clock64();
         if (q >= 2 && seq_on) {
             const int j = (q - 2) * 32 + lane;
-            const float vr = __ldg(a.wc[ly] + 64 + j) * DF_NL2E, br = __ldg(a.bias[ly] + 64 + j);
+            const float vr = __ldg(a.wc[ly] + 64 + j) * df_prescale<GATE>(), br = __ldg(a.bias[ly] + 64 + j);
             const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
             unsigned char* hb = hbuf + (j >> 2) * DF_LBO + 7 * 16 + (j & 3) * 4;
             const float* csj = cs + j;
@@ -366,11 +399,11 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
                 if (m <= m_chi) mbar_wait(chunk_bar + (sw * 2 + (q - 2)) * 16 + m, ly & 1);
                 const bool full = 16 * m >= p_lo && 16 * m + 16 <= p_hi;
                 if (full) {
-                    if (ly == 0) df_hchunk<true, true>(tl, m, q == 3, p_lo, p_hi, p_end, vr, br, csj, hb);
-                    else df_hchunk<true, false>(tl, m, q == 3, p_lo, p_hi, p_end, vr, br, csj, hb);
+                    if (ly == 0) df_hchunk<true, true, GATE>(tl, m, q == 3, p_lo, p_hi, p_end, vr, br, csj, hb);
+                    else df_hchunk<true, false, GATE>(tl, m, q == 3, p_lo, p_hi, p_end, vr, br, csj, hb);
                 } else {
-                    if (ly == 0) df_hchunk<false, true>(tl, m, q == 3, p_lo, p_hi, p_end, vr, br, csj, hb);
-                    else df_hchunk<false, false>(tl, m, q == 3, p_lo, p_hi, p_end, vr, br, csj, hb);
+                    if (ly == 0) df_hchunk<false, true, GATE>(tl, m, q == 3, p_lo, p_hi, p_end, vr, br, csj, hb);
+                    else df_hchunk<false, false, GATE>(tl, m, q == 3, p_lo, p_hi, p_end, vr, br, csj, hb);
                 }
             }
         }
@@ -437,16 +470,26 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
-inline cudaError_t launch_dprnn_fused(const DfArgs& a, cudaStream_t st) {
+template <int GATE>
+inline cudaError_t launch_dprnn_fused_g(const DfArgs& a, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(dprnn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(dprnn_fused_kernel<GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int tiles = (a.nseq_total + a.nseq_tile - 1) / a.nseq_tile;
-    dprnn_fused_kernel<<<tiles, DF_NT, DF_SMEM, st>>>(a);
+    dprnn_fused_kernel<GATE><<<tiles, DF_NT, DF_SMEM, st>>>(a);
     return cudaGetLastError();
+}
+inline cudaError_t launch_dprnn_fused(const DfArgs& a, cudaStream_t st) {
+    static const int gate = [] {
+        const char* v = getenv("RTFS_DF_GATE");  // A/B of the gate arithmetic (see df_gate); tanh.approx measured parity-neutral
+        return v ? atoi(v) : 1;
+    }();
+    if (gate == 1) return launch_dprnn_fused_g<1>(a, st);
+    if (gate == 2) return launch_dprnn_fused_g<2>(a, st);
+    return launch_dprnn_fused_g<0>(a, st);
 }
 
 }  // namespace rtfs

@@ -16,6 +16,7 @@
 //
 //   out[t][f][c] = bias[c] + sum_{i,j<4} w[c][i][j] * X[S*t-1+i][S*f-1+j][c]   (zero outside), S = 1 (or 2 for DUAL's second output)
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 
 namespace rtfs {
@@ -101,7 +102,7 @@ struct XrGln {
     DEVINL void issue(int r, float* slot, int tid, int nthreads) const { dr_issue_row(slot, base_ + (long long)r * Fi * 64, Fi, tid, nthreads); }
     DEVINL float2 fetch(const float* slot, int q) const {
         const float2 v = *reinterpret_cast<const float2*>(slot + dr_phys(f0_ - 1 + q) * 16 + 2 * pair_);
-        float2 y = make_float2(fmaf(v.x, sc_.x, sh_.x), fmaf(v.y, sc_.y, sh_.y));
+        float2 y = __ffma2_rn(v, sc_, sh_);
         if (ACT == 2) {
             y.x = prelu(y.x, a_);
             y.y = prelu(y.y, a_);
@@ -188,6 +189,144 @@ struct DrArgs {
 // NT threads = 8 channel pairs x NT/8 strips of 4 columns  (NT/8 >= ceil(Fi/4))
 template <class XF, int NW, bool DUAL, int NT>
 __global__ void __launch_bounds__(NT, (NT > 256 ? 2 : 4)) dwroll_kernel(XF xf, DrArgs<NW> a) {
+    constexpr int NCONV = NW + (DUAL ? 1 : 0);
+    extern __shared__ __align__(16) float dr_smem[];
+    __shared__ float wsm[NCONV][16][DR_CG];  // filter taps of this channel group
+    __shared__ float bsm[NCONV][DR_CG];
+    __shared__ float scratch[2 * (NT / 32)];
+
+    const int tid = threadIdx.x, pair = tid & 7, strip = tid >> 3;
+    const int cg = blockIdx.x & 3, seg = blockIdx.x >> 2, b = blockIdx.y;
+    const int Ti = a.Ti, Fi = a.Fi;
+    const int f0 = 4 * strip;
+    const bool active = f0 < Fi;
+    const int t0 = seg * a.rows_per_seg;
+    const int t1 = min(t0 + a.rows_per_seg, Ti);
+    const int slot_fl = xf.slot_floats();
+
+    for (int i = tid; i < NCONV * 16 * DR_CG; i += NT) {
+        const int w = i / (16 * DR_CG), rem = i - w * 16 * DR_CG, tap = rem / DR_CG, c = rem - tap * DR_CG;
+        const float* wp = (DUAL && w == NW) ? a.w2 : a.w[w < NW ? w : 0];
+        wsm[w][tap][c] = __ldg(wp + tap * 64 + cg * DR_CG + c);
+    }
+    for (int i = tid; i < NCONV * DR_CG; i += NT) {
+        const int w = i / DR_CG, c = i - w * DR_CG;
+        const float* bp = (DUAL && w == NW) ? a.bias2 : a.bias[w < NW ? w : 0];
+        bsm[w][c] = bp ? __ldg(bp + cg * DR_CG + c) : 0.f;
+    }
+    xf.init(b, cg, pair, active ? f0 : 0);
+
+    // input rows r = t0-1 .. t1+1 ; row r lives in slot (r - (t0-1)) % DR_NR
+    const int r_first = t0 - 1, r_last = t1 + 1;
+    auto issue = [&](int r) {
+        if (r >= 0 && r < Ti && r <= r_last) xf.issue(r, dr_smem + ((r - r_first) % DR_NR) * slot_fl, tid, NT);
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < DR_NR - 1; ++i) issue(r_first + i);
+
+    // win[slot][q]: 4 input rows x 7 columns (f0-1 .. f0+5).  The row loop is unrolled by 4 so that the slot a new
+    // row lands in (step & 3) and the logical window order are compile-time: no register moves when the window rolls.
+    float2 win[4][7];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 7; ++q) win[i][q] = make_float2(0.f, 0.f);
+    float2 st_s[NCONV], st_q[NCONV];  // per channel of the pair; packed f32x2 math (FFMA2) throughout
+#pragma unroll
+    for (int w = 0; w < NCONV; ++w) st_s[w] = st_q[w] = make_float2(0.f, 0.f);
+
+    const int wT = 2 + (Ti & 1), wF = 2 + (Fi & 1);
+    const float pool_scale = 1.f / (float)(wT * wF);
+    const int c0 = cg * DR_CG + 2 * pair;
+
+    for (int rb = r_first; rb <= r_last; rb += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = rb + k;
+            if (r > r_last) break;       // uniform over the CTA
+            cp_async_wait<DR_NR - 2>();  // this thread's pieces of row r have landed
+            __syncthreads();             // everyone's have; everyone is done reading row r-1's slot
+            issue(r + DR_NR - 1);        // -> into the slot of row r-1
+            const bool rvalid = r >= 0 && r < Ti;
+            const float* slot = dr_smem + ((r - r_first) % DR_NR) * slot_fl;
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                const int f = f0 - 1 + q;
+                win[k][q] = (active && rvalid && f >= 0 && f < Fi) ? xf.fetch(slot, q) : make_float2(0.f, 0.f);
+            }
+            const int t = r - 2;  // output row whose window (rows t-1..t+2) is now complete
+            if (t < t0 || !active) continue;
+            // logical window row i (input row t-1+i) = win[(k + 1 + i) & 3]
+            // ---- stride-1 outputs
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                float2 acc[4];
+                const float2 bs = *reinterpret_cast<const float2*>(&bsm[w][2 * pair]);
+#pragma unroll
+                for (int o = 0; o < 4; ++o) acc[o] = bs;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 wv = *reinterpret_cast<const float2*>(&wsm[w][i * 4 + j][2 * pair]);
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) acc[o] = __ffma2_rn(wv, win[(k + 1 + i) & 3][o + j], acc[o]);
+                    }
+                float* orow = a.out[w] + (((long long)b * Ti + t) * Fi + f0) * 64 + c0;
+#pragma unroll
+                for (int o = 0; o < 4; ++o)
+                    if (f0 + o < Fi) {
+                        *reinterpret_cast<float2*>(orow + o * 64) = acc[o];
+                        st_s[w] = __fadd2_rn(st_s[w], acc[o]);
+                        st_q[w] = __ffma2_rn(acc[o], acc[o], st_q[w]);
+                    }
+            }
+            // ---- stride-2 output row t/2 and the adaptive average pool
+            if (DUAL && (t & 1) == 0 && (t >> 1) < a.To2) {
+                const int to = t >> 1;
+                const float2 bs = *reinterpret_cast<const float2*>(&bsm[NW][2 * pair]);
+                float2 acc[2] = {bs, bs};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 wv = *reinterpret_cast<const float2*>(&wsm[NW][i * 4 + j][2 * pair]);
+#pragma unroll
+                        for (int o = 0; o < 2; ++o) acc[o] = __ffma2_rn(wv, win[(k + 1 + i) & 3][2 * o + j], acc[o]);
+                    }
+#pragma unroll
+                for (int o = 0; o < 2; ++o) {
+                    const int fo = (f0 >> 1) + o;
+                    if (fo < a.Fo2) {
+                        const long long off = (((long long)b * a.To2 + to) * a.Fo2 + fo) * 64 + c0;
+                        *reinterpret_cast<float2*>(a.out2 + off) = acc[o];
+                        st_s[NW] = __fadd2_rn(st_s[NW], acc[o]);
+                        st_q[NW] = __ffma2_rn(acc[o], acc[o], st_q[NW]);
+                        float2 p = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int i = 1; i < 4; ++i)
+#pragma unroll
+                            for (int j = 1; j < 4; ++j)
+                                if (i <= wT && j <= wF) p = __fadd2_rn(p, win[(k + 1 + i) & 3][2 * o + j]);
+                        *reinterpret_cast<float2*>(a.pool + off) = make_float2(p.x * pool_scale, p.y * pool_scale);
+                    }
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int w = 0; w < NCONV; ++w) {
+        double* dst = (DUAL && w == NW) ? a.sums2 : a.sums[w < NW ? w : 0];
+        block_stats_atomic(st_s[w].x + st_s[w].y, st_q[w].x + st_q[w].y, dst ? dst + 2 * b : nullptr, scratch);
+    }
+}
+
+// First version of the rolling kernel (scalar FFMA, window rolled with register moves); still the faster one for the
+// TF-AR input functor at full resolution, where the packed version spills.
+template <class XF, int NW, bool DUAL, int NT>
+__global__ void __launch_bounds__(NT, (NT > 256 ? 2 : 4)) dwroll_scalar_kernel(XF xf, DrArgs<NW> a) {
     constexpr int NCONV = NW + (DUAL ? 1 : 0);
     extern __shared__ __align__(16) float dr_smem[];
     __shared__ float wsm[NCONV][16][DR_CG];  // filter taps of this channel group
@@ -349,9 +488,9 @@ inline int dr_rows_per_seg(int T, int B, int ctas_per_sm) {
     return best;
 }
 
-template <class XF, int NW, bool DUAL, int NT>
+template <class XF, int NW, bool DUAL, int NT, bool PACKED = true>
 inline cudaError_t launch_dwroll(const XF& xf, DrArgs<NW> a, int B, cudaStream_t st) {
-    auto kern = dwroll_kernel<XF, NW, DUAL, NT>;
+    auto kern = PACKED ? dwroll_kernel<XF, NW, DUAL, NT> : dwroll_scalar_kernel<XF, NW, DUAL, NT>;
     const int smem = DR_NR * xf.slot_floats() * 4;
     static int configured = 0;
     if (smem > configured) {
@@ -359,7 +498,11 @@ inline cudaError_t launch_dwroll(const XF& xf, DrArgs<NW> a, int B, cudaStream_t
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    a.rows_per_seg = dr_rows_per_seg(a.Ti, B, 2);
+    static const int rows_env = [] {
+        const char* v = getenv("RTFS_DW_ROWS");  // tuning override: output rows per CTA
+        return v ? atoi(v) : 0;
+    }();
+    a.rows_per_seg = rows_env > 0 ? (rows_env < a.Ti ? rows_env : a.Ti) : (a.Ti >= 96 ? 32 : dr_rows_per_seg(a.Ti, B, 2));  // 32: measured best at T = 251 (A/B of 16..126)
     const int nseg = (a.Ti + a.rows_per_seg - 1) / a.rows_per_seg;
     kern<<<dim3(4 * nseg, B), NT, smem, st>>>(xf, a);
     return cudaGetLastError();
