@@ -23,7 +23,11 @@ def init(backend=None):
         os.environ.setdefault("MASTER_PORT", "29500")
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
-        dist.init_process_group(backend, rank=rank, world_size=world)
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            kw["device_id"] = torch.device("cuda", local_rank)  # binds the communicator to this rank's GPU (no guessing)
+        dist.init_process_group(backend, rank=rank, world_size=world, **kw)
     return rank, local_rank, world
 
 
