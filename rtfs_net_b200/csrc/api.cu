@@ -16,6 +16,7 @@
 #include "gemm.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tcp.cuh"
+#include "gateproj_wide.cuh"
 
 using namespace rtfs;
 
@@ -232,7 +233,7 @@ int run_bottleneck(const Ctx& c, const float* a0, float* a1, bool compute_stats)
     STAGE(RTFS_SG_BOTTLENECK);
     if (use_tc()) {
         StoreEpi4 ep{a1, 256, c.P[RTFS_P_BN_B]};
-        if (use_persistent(0)) CK((launch_gemm_tcp<256, 256, 4, 3, false, 3, false>(al, c.P[RTFS_P_BN_WI], ep, (int)(d.B * d.P), c.st)));
+        if (use_persistent(0)) CK((launch_gemm_tcp<256, 256, 4, 3, false, 4, 2, 512>(al, c.P[RTFS_P_BN_WI], ep, (int)(d.B * d.P), c.st)));
         else CK((launch_gemm_tc<256, 256, 3, 1, 4, 256>(al, c.P[RTFS_P_BN_WI], ep, (int)(d.B * d.P), c.st)));
     } else {
         StoreEpi ep{a1, 256, c.P[RTFS_P_BN_B]};
@@ -484,9 +485,12 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out, boo
     {
         GateLoader al{x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], 256};
         STAGE(RTFS_SG_GATE_PROJ);
-        if (use_tc()) {
+        if (use_tc() && env_flag("RTFS_GATE_WIDE")) {  // 1024-thread lock-step variant: correct, but measured slower (0.58 vs 0.43 ms)
+            GwArgs ga{x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], P[RTFS_P_PJ_WI], P[RTFS_P_PJ_B], p_pre, c.stat(RTFS_ST_PJ), M, (int)d.P, d.B, 0};
+            CK(launch_gateproj_wide(ga, c.st));
+        } else if (use_tc()) {
             StatsEpi4 ep{p_pre, 64, P[RTFS_P_PJ_B], c.stat(RTFS_ST_PJ), (int)d.P, d.B};
-            if (use_persistent(1)) CK((launch_gemm_tcp<64, 256, 7, 1, true, 2, true>(al, P[RTFS_P_PJ_WI], ep, M, c.st)));
+            if (use_persistent(1)) CK((launch_gemm_tcp<64, 256, 6, 1, true, 4, 2, 512>(al, P[RTFS_P_PJ_WI], ep, M, c.st)));
                         else CK((launch_gemm_tc<64, 256, 4, 2, 2, 256>(al, P[RTFS_P_PJ_WI], ep, M, c.st)));
         } else {
             StatsEpi ep{p_pre, 64, P[RTFS_P_PJ_B], c.stat(RTFS_ST_PJ), (int)d.P, d.B};
@@ -646,7 +650,7 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out, boo
             CK((launch_gemm_tc<256, 64, 2, 2, 2, 512>(al, P[RTFS_P_RC_WI], ep, M, c.st)));
         } else if (use_tc()) {
             ResidOutEpi4 ep{out, P[RTFS_P_RC_B], x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], addend, 0.f};
-            if (use_persistent(2)) CK((launch_gemm_tcp<256, 64, 4, 1, true, 2, false>(al, P[RTFS_P_RC_WI], ep, M, c.st)));
+            if (use_persistent(2)) CK((launch_gemm_tcp<256, 64, 4, 1, true, 2, 0, 256>(al, P[RTFS_P_RC_WI], ep, M, c.st)));
             else if (use_wide()) CK((launch_gemm_tc<256, 64, 2, 2, 2, 512>(al, P[RTFS_P_RC_WI], ep, M, c.st)));
             else CK((launch_gemm_tc<256, 64, 2, 2, 2, 256>(al, P[RTFS_P_RC_WI], ep, M, c.st)));
         } else {
@@ -698,7 +702,7 @@ int run_mask(const Ctx& c, const float* refined, const float* a0, float* z) {
     STAGE(RTFS_SG_MASK);
     if (use_tc()) {
         MaskEpi4 ep{z, c.P[RTFS_P_MK_B], a0};
-        if (use_persistent(3)) CK((launch_gemm_tcp<256, 256, 4, 3, false, 3, false>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
+        if (use_persistent(3)) CK((launch_gemm_tcp<256, 256, 4, 3, false, 4, 2, 512>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
         else CK((launch_gemm_tc<256, 256, 3, 1, 4, 256>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
     } else {
         MaskEpi ep{z, c.P[RTFS_P_MK_B], a0};

@@ -13,6 +13,7 @@
 // functor sees float4 pieces of rows, so every global access of the epilogue is a coalesced 128-byte row
 // segment (bias / residual / gateway recompute / complex mask / gLN statistics fused as before).
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -453,11 +454,12 @@ __global__ void __launch_bounds__(NT, MINB) gemm_tc_kernel(AL al, const float* _
             v.w = tf32r(v.w);
             *reinterpret_cast<float4*>(a_dst0 + (size_t)s * TC_A_STAGE + i * (RS * 16)) = v;
         }
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy (issued BEFORE the next
+                              // chunk's loads so that it does not wait behind them)
         if (kc + PF < NK) {
 #pragma unroll
             for (int i = 0; i < RPT; ++i) areg[kc % PF][i] = al.load(i, (kc + PF) * TC_KC + kq * 4);
         }
-        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
         __syncthreads();
         if (tid == 0) {
             mbar_wait(full_w + s, (kc / NS) & 1);

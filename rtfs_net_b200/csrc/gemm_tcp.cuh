@@ -13,13 +13,13 @@
 //   warp 17     weights  : WRES: the whole image (<= 64 KB) is bulk-copied once and stays resident;
 //                          otherwise 32-wide K slabs stream through an NSW-stage ring (cp.async.bulk + mbarrier)
 #pragma once
+#include <cstdio>
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
 namespace rtfs {
 
-constexpr int TCP_THREADS = 576;
-constexpr int TCP_EPI = 256, TCP_PROD = 256;
+constexpr int TCP_EPI = 256;  // epilogue threads (warps 0-7); then NPROD producer threads, the MMA warp and the weight warp
 
 DEVINL void mbar_arrive_cta(uint64_t* bar) {
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -31,10 +31,19 @@ __host__ __device__ constexpr int tcp_smem_bytes(int extra_floats) {
 }
 
 // EPS: epilogue functor exposes finish_group(scratch, gtid, nthr, barid) (gLN statistics) instead of finish()
-// ASYNC: the producers land the raw A chunk in its ring stage with 16-byte cp.async (NSA-2 chunks = ~100 KB in flight
-// per SM, no registers tied up, running ahead across tile boundaries) and apply the loader's transform in place.
-template <int BN, int KTOT, int NSA, int NSW, bool WRES, int PF, bool ASYNC, class AL, class EP>
-__global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(AL al, const float* __restrict__ Wimg, EP ep, int M, int ntiles) {
+// Producer modes (template parameter ASYNC):
+//   0  per-tile register pipeline through the loader functor's load() (any loader; PF chunks in flight, drains at tile ends)
+//   1  raw chunk landed in its ring stage with 16-byte cp.async, transformed in place -- measured SLOWER: LDGSTS streams at
+//      ~3.4 TB/s on this part whatever the depth (tools/probe/cpasync_probe.cu), plain loads at 5.7-5.9 TB/s
+//   2  flat raw register stream: PF chunks of RAW values in flight per thread, running ahead across tile boundaries;
+//      the loader's xform() is applied when a chunk is stored (loaders with raw()/xform(): gLN-act, gateway, PReLU)
+template <int BN, int KTOT, int NSA, int NSW, bool WRES, int PF, int ASYNC, int NPROD, class AL, class EP>
+__global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al, const float* __restrict__ Wimg, EP ep, int M, int ntiles) {
+    constexpr int TCP_PROD = NPROD;             // 256 or 512 producer threads
+    constexpr int RPT = 1024 / NPROD;           // A rows per producer thread per chunk
+    constexpr int RS = NPROD / 8;               // row stride between them
+    constexpr int MMA_WARP = (TCP_EPI + NPROD) / 32;
+    static_assert(NPROD == 256 || NPROD == 512, "8 or 16 producer warps");
     constexpr int NK = KTOT / TC_KC;
     constexpr int WBYTES = BN * 128;
     constexpr int NWS = WRES ? NK : NSW;  // weight slabs held in shared memory
@@ -61,7 +70,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(AL al, const f
     if (warp == 0) tmem_alloc<(2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512)>(tmem_slot);
     if (tid == 32) {
         for (int s = 0; s < NSA; ++s) {
-            mbar_init(full_a + s, TCP_PROD);
+            mbar_init(full_a + s, TCP_PROD / 32);  // one elected arrive per producer warp
             mbar_init(empty_a + s, 1);
         }
         for (int s = 0; s < NWS; ++s) {
@@ -70,7 +79,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(AL al, const f
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tmem_full + s, 1);
-            mbar_init(tmem_empty + s, TCP_EPI);
+            mbar_init(tmem_empty + s, TCP_EPI / 32);
         }
         fence_mbar_init();
     }
@@ -123,17 +132,18 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(AL al, const f
                 __syncwarp();
             }
             tc_fence_before();
-            mbar_arrive_cta(tmem_empty + acc);  // this thread's TMEM reads of the accumulator are complete
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(tmem_empty + acc);  // this warp's TMEM reads of the accumulator are complete
             ep.finish_group(scratch, tid, TCP_EPI, 1);
         }
-    } else if (warp < 16) {
+    } else if (warp < MMA_WARP) {
         // ================================================================= A producers
         const int ptid = tid - TCP_EPI;
         const int kq = ptid & 7;
         unsigned char* a_dst0 = a_stage + kq * TC_LBO_A + (ptid >> 3) * 16;
-        if constexpr (ASYNC) {
-            constexpr int D = NSA - 2;  // chunks in flight ahead of the transform
-            static_assert(!ASYNC || NSA >= 3, "async producers need >= 3 stages");
+        if constexpr (ASYNC == 1) {
+            constexpr int D = NSA - 2 - (NSA >= 7 ? 2 : 0);  // chunks in flight ahead of the transform (slack for the commit -> empty round trip)
+            static_assert(NSA >= 3, "async producers need >= 3 stages");
             const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
             const int G = my_tiles * NK;
             auto issue = [&](int g) {
@@ -143,10 +153,10 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(AL al, const f
                     const int s = g % NSA;
                     if (g >= NSA) mbar_wait(empty_a + s, ((g / NSA) - 1) & 1);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const long long row = rbase + 32 * i;
+                    for (int i = 0; i < RPT; ++i) {
+                        const long long row = rbase + RS * i;
                         const bool valid = row < M;
-                        cp_async16(a_dst0 + (size_t)s * TC_A_STAGE + i * (32 * 16), al.raw(valid ? row : 0, kc * TC_KC + kq * 4), valid);
+                        cp_async16(a_dst0 + (size_t)s * TC_A_STAGE + i * (RS * 16), al.raw(valid ? row : 0, kc * TC_KC + kq * 4), valid);
                     }
                 }
                 cp_async_commit();
@@ -164,9 +174,9 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(AL al, const f
                 }
                 const int s = g % NSA;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float4* slot = reinterpret_cast<float4*>(a_dst0 + (size_t)s * TC_A_STAGE + i * (32 * 16));
-                    const int row = row0 + (ptid >> 3) + 32 * i;
+                for (int i = 0; i < RPT; ++i) {
+                    float4* slot = reinterpret_cast<float4*>(a_dst0 + (size_t)s * TC_A_STAGE + i * (RS * 16));
+                    const int row = row0 + (ptid >> 3) + RS * i;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (row < M) v = al.xform(*slot, row, kc * TC_KC + kq * 4);
                     v.x = tf32r(v.x);
@@ -176,44 +186,92 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(AL al, const f
                     *slot = v;
                 }
                 fence_proxy_async();
-                mbar_arrive_cta(full_a + s);
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cta(full_a + s);
             }
             cp_async_wait<0>();
+        } else if constexpr (ASYNC == 2) {
+            const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+            const int G = my_tiles * NK;
+            float4 raw[PF][RPT];
+            auto fetch = [&](int g, float4 (&dst)[RPT]) {
+                const int it = g / NK, kc = g - it * NK;
+                const long long rbase = (long long)(blockIdx.x + it * gridDim.x) * TC_BM + (ptid >> 3);
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) {
+                    const long long row = rbase + RS * i;
+                    dst[i] = row < M ? ldg4(al.raw(row, kc * TC_KC + kq * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+#pragma unroll
+            for (int c = 0; c < PF; ++c)
+                if (c < G) fetch(c, raw[c]);
+            for (int g0 = 0; g0 < G; g0 += PF) {
+#pragma unroll
+                for (int j = 0; j < PF; ++j) {
+                    const int g = g0 + j;
+                    if (g >= G) break;
+                    const int it = g / NK, kc = g - it * NK;
+                    const int row0 = (blockIdx.x + it * gridDim.x) * TC_BM;
+                    if (kc == 0) {
+                        al.init_p(row0, M, extra + (it & 1) * AL::kExtra, ptid, TCP_PROD);
+                        if (AL::kExtra > 0) named_bar_sync(2, TCP_PROD);
+                    }
+                    const int s = g % NSA;
+                    if (g >= NSA) mbar_wait(empty_a + s, ((g / NSA) - 1) & 1);
+#pragma unroll
+                    for (int i = 0; i < RPT; ++i) {
+                        const int row = row0 + (ptid >> 3) + RS * i;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row < M) v = al.xform(raw[j][i], row, kc * TC_KC + kq * 4);
+                        v.x = tf32r(v.x);
+                        v.y = tf32r(v.y);
+                        v.z = tf32r(v.z);
+                        v.w = tf32r(v.w);
+                        *reinterpret_cast<float4*>(a_dst0 + (size_t)s * TC_A_STAGE + i * (RS * 16)) = v;
+                    }
+                    fence_proxy_async();  // before the next loads are issued
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cta(full_a + s);
+                    if (g + PF < G) fetch(g + PF, raw[j]);
+                }
+            }
         } else {
         int it = 0, ga = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int row0 = tile * TC_BM;
             al.init_p(row0, M, extra + (it & 1) * AL::kExtra, ptid, TCP_PROD);
             if (AL::kExtra > 0) named_bar_sync(2, TCP_PROD);  // the tile's loader table is complete
-            float4 areg[PF][4];
+            float4 areg[PF][RPT];
 #pragma unroll
             for (int c = 0; c < PF; ++c) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) areg[c][i] = al.load(i, c * TC_KC + kq * 4);
+                for (int i = 0; i < RPT; ++i) areg[c][i] = al.load(i, c * TC_KC + kq * 4);
             }
 #pragma unroll
             for (int kc = 0; kc < NK; ++kc, ++ga) {
                 const int s = ga % NSA, use = ga / NSA;
                 if (use > 0) mbar_wait(empty_a + s, (use - 1) & 1);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < RPT; ++i) {
                     float4 v = areg[kc % PF][i];
                     v.x = tf32r(v.x);
                     v.y = tf32r(v.y);
                     v.z = tf32r(v.z);
                     v.w = tf32r(v.w);
-                    *reinterpret_cast<float4*>(a_dst0 + (size_t)s * TC_A_STAGE + i * (32 * 16)) = v;
+                    *reinterpret_cast<float4*>(a_dst0 + (size_t)s * TC_A_STAGE + i * (RS * 16)) = v;
                 }
+                fence_proxy_async();  // before the next loads are issued
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cta(full_a + s);
                 if (kc + PF < NK) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) areg[kc % PF][i] = al.load(i, (kc + PF) * TC_KC + kq * 4);
+                    for (int i = 0; i < RPT; ++i) areg[kc % PF][i] = al.load(i, (kc + PF) * TC_KC + kq * 4);
                 }
-                fence_proxy_async();
-                mbar_arrive_cta(full_a + s);
             }
         }
         }
-    } else if (warp == 16) {
+    } else if (warp == MMA_WARP) {
         // ================================================================= MMA issuer
         if (lane == 0) {
             int it = 0, ga = 0;
@@ -268,9 +326,9 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) gemm_tcp_kernel(AL al, const f
     if (warp == 0) tmem_dealloc<(2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512)>(tmem);
 }
 
-template <int BN, int KTOT, int NSA, int NSW, bool WRES, int PF, bool ASYNC, class AL, class EP>
+template <int BN, int KTOT, int NSA, int NSW, bool WRES, int PF, int ASYNC, int NPROD, class AL, class EP>
 inline cudaError_t launch_gemm_tcp(const AL& al, const float* Wimg, const EP& ep, int M, cudaStream_t st) {
-    auto kern = gemm_tcp_kernel<BN, KTOT, NSA, NSW, WRES, PF, ASYNC, AL, EP>;
+    auto kern = gemm_tcp_kernel<BN, KTOT, NSA, NSW, WRES, PF, ASYNC, NPROD, AL, EP>;
     const int smem = tcp_smem_bytes<BN, KTOT, NSA, NSW, WRES>(AL::kExtra);
     static bool configured = false;
     if (!configured) {
@@ -280,7 +338,7 @@ inline cudaError_t launch_gemm_tcp(const AL& al, const float* Wimg, const EP& ep
     }
     const int ntiles = (M + TC_BM - 1) / TC_BM;
     const int grid = ntiles < 148 ? ntiles : 148;
-    kern<<<grid, TCP_THREADS, smem, st>>>(al, Wimg, ep, M, ntiles);
+    kern<<<grid, TCP_EPI + NPROD + 64, smem, st>>>(al, Wimg, ep, M, ntiles);
     return cudaGetLastError();
 }
 
