@@ -15,6 +15,7 @@ DualPathRNN(dim 3), MultiHeadSelfAttention2D], ATTNFusion, MaskGenerator with RI
 accelerated; other reference configurations raise NotImplementedError at construction.
 """
 import math
+import os
 import sys
 
 import torch
@@ -507,6 +508,7 @@ class _Runtime:
         self._key = None
         self._ws = None
         self._ws_key = None
+        self._vgraph = {}  # (device, shape, parameter key) -> (CUDAGraph, static input, static output) of the video block
 
     # ---------------------------------------------------------------- plumbing
     def _check(self, *tensors):
@@ -662,6 +664,35 @@ class _Runtime:
             _lib.check(_lib.lib().rtfs_decoder_forward(P.ptr, zz.data_ptr(), out.data_ptr(), ws.data_ptr(), zz.shape[0], L, self._stream()), "rtfs_decoder_forward")
         return out.view(B, -1, L)
 
+    # ---------------------------------------------------------------- video (VP) block
+    def video_block(self, mouth):
+        """The VP block (tdanet.py:106-133 in 1-D, attention.py:9-73,192-220) is ~150 launch-bound torch library ops on
+        (B,512,Tv) tensors: captured once per (shape, parameter version) into a CUDA graph and replayed.
+        RTFS_NO_VIDEO_GRAPH=1 runs it eagerly."""
+        rm = self.model.refinement_module
+        if os.environ.get("RTFS_NO_VIDEO_GRAPH"):
+            return rm.video_net.get_block(0)(self.model.video_bottleneck(mouth)).contiguous()
+        key = (str(mouth.device), tuple(mouth.shape), self._key)
+        ent = self._vgraph.get(key)
+        if ent is None:
+            self._vgraph.clear()
+            static_in = mouth.detach().clone()
+            side = torch.cuda.Stream(device=mouth.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up on a side stream (lazy cuDNN / cuBLAS initialisation) before capture
+                for _ in range(2):
+                    rm.video_net.get_block(0)(self.model.video_bottleneck(static_in))
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = rm.video_net.get_block(0)(self.model.video_bottleneck(static_in)).contiguous()
+            ent = (graph, static_in, static_out)
+            self._vgraph[key] = ent
+        graph, static_in, static_out = ent
+        static_in.copy_(mouth)
+        graph.replay()
+        return static_out
+
     # ---------------------------------------------------------------- whole forward (one C call)
     def forward(self, wav, mouth):
         if wav.ndim == 1:
@@ -675,7 +706,7 @@ class _Runtime:
         R = rm.audio_params["repeats"]
         with torch.cuda.device(wav.device):
             P = self.params(wav.device)
-            video = rm.video_net.get_block(0)(self.model.video_bottleneck(mouth)).contiguous()
+            video = self.video_block(mouth.contiguous())
             Tv = video.shape[-1]
             ws = self.workspace(B, L, Tv, wav.device)
             out = torch.empty(B, L, device=wav.device, dtype=torch.float32)
