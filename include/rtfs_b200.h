@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RTFS_ABI_VERSION 3
+#define RTFS_ABI_VERSION 4
 #define RTFS_F 129
 #define RTFS_FC 64
 
@@ -76,6 +76,7 @@ enum rtfs_param {
     /* fused dual-path RNN kernel: 52 slabs of 16 KB = SRU layer 0 (32), layers 1-3 (4 each), ConvTranspose1d (8),
      * SRU slabs = [acc 2][K piece 4][TMEM lane 128][4] with lanes (candidate | reset) and (forget | highway) */
     RTFS_P_RF_FUSED, RTFS_P_RT_FUSED,
+    RTFS_P_ENC_WI3, /* encoder conv, 3xTF32 split: image of [W_hi | W_hi | W_lo] (K = 96) */
     RTFS_P_COUNT
 };
 

@@ -216,9 +216,15 @@ int run_encoder(const Ctx& c, const float* wav, float* a0, int L) {
     }
     CKN(cudaMemsetAsync(c.stat(RTFS_ST_A0), 0, sizeof(double) * 2 * d.B, c.st));
     Im2colLoader al{c.buf(RTFS_WS_SPEC), d.T, d.F};
-    StatsEpi ep{a0, 256, nullptr, c.stat(RTFS_ST_A0), (int)d.P, d.B};
     STAGE(RTFS_SG_ENC_CONV);
-    CK((launch_gemm<128, 32, true>(al, c.P[RTFS_P_ENC_W], ep, (int)(d.B * d.P), 256, c.st)));
+    if (use_tc() && !env_flag("RTFS_LEGACY_ENC")) {
+        Im2colLoader3x al3{al};
+        StatsEpi4 ep{a0, 256, nullptr, c.stat(RTFS_ST_A0), (int)d.P, d.B, 0, 0, 0.f, 0.f, 0.f, 0.f};
+        CK((launch_gemm_tcp<256, 96, 4, 1, true, 3, 0, 256>(al3, c.P[RTFS_P_ENC_WI3], ep, (int)(d.B * d.P), c.st)));
+    } else {
+        StatsEpi ep{a0, 256, nullptr, c.stat(RTFS_ST_A0), (int)d.P, d.B};
+        CK((launch_gemm<128, 32, true>(al, c.P[RTFS_P_ENC_W], ep, (int)(d.B * d.P), 256, c.st)));
+    }
     return 0;
 }
 

@@ -279,6 +279,26 @@ struct Im2colLoader {
     }
 };
 
+// Error-compensated (3xTF32) variant for the tcgen05 kernels: K' = 96 = [hi | lo | hi] of the 32 im2col columns, to be
+// multiplied with the weight image [W_hi | W_hi | W_lo]: hi.W_hi + lo.W_hi + hi.W_lo accumulates in fp32.
+struct Im2colLoader3x {
+    Im2colLoader base;
+    static constexpr int kExtra = 0;
+    DEVINL void init(int row0, int M, float* e) { base.init(row0, M, e); }
+    DEVINL void init_p(int row0, int M, float*, int ptid, int nthr) {
+        base.row0_ = row0 + (ptid >> 3);
+        base.rs_ = nthr >> 3;
+        base.M_ = M;
+    }
+    DEVINL float4 load(int i, int k) const {
+        const int seg = k >> 5;
+        const float4 v = base.load(i, k & 31);
+        const float4 hi = make_float4(tf32r(v.x), tf32r(v.y), tf32r(v.z), tf32r(v.w));
+        if (seg != 1) return hi;
+        return make_float4(tf32r(v.x - hi.x), tf32r(v.y - hi.y), tf32r(v.z - hi.z), tf32r(v.w - hi.w));
+    }
+};
+
 // ====================================================================== epilogues
 // contract: init(row0, M); store(row, col, v0, v1) for (row,col),(row,col+1); finish(scratch) by all threads
 struct StoreEpi {
