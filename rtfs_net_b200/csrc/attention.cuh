@@ -36,8 +36,8 @@ __global__ void __launch_bounds__(128) rowblock_ln_kernel(RowblockArgs a) {
     extern __shared__ __align__(16) float sm[];
     float* Xs = sm;                  // [64][LD]
     float* Wsm = Xs + 64 * LD;       // [N][LD]
-    float* Ys = Wsm + N * LD;        // [64][LDY]
-    float* stat = Ys + 64 * LDY;     // [12][2]
+    float* Ys = sm;                  // [64][LDY]  aliases Xs/Wsm once the MMAs have consumed them (more CTAs per SM)
+    float* stat = sm + ((64 + N) * LD > 64 * LDY ? (64 + N) * LD : 64 * LDY);  // [12][2]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const long long bt = blockIdx.x;
     const float* xin = a.x + bt * (64 * 64);
@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(128) rowblock_ln_kernel(RowblockArgs a) {
             mma_tf32(acc[ni], af, bf);
         }
     }
+    __syncthreads();  // every warp is done reading Xs / Wsm: Ys may overwrite them
     // bias + PReLU -> Ys
 #pragma unroll
     for (int ni = 0; ni < NI; ++ni) {
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(128) rowblock_ln_kernel(RowblockArgs a) {
 
 template <int N>
 constexpr int rowblock_smem_floats() {
-    return 64 * 68 + N * 68 + 64 * (N + 1) + 32;
+    return ((64 + N) * 68 > 64 * (N + 1) ? (64 + N) * 68 : 64 * (N + 1)) + 32;
 }
 
 // ---------------------------------------------------------------- attention core
