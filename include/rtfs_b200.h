@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RTFS_ABI_VERSION 4
+#define RTFS_ABI_VERSION 5
 #define RTFS_F 129
 #define RTFS_FC 64
 
@@ -77,6 +77,7 @@ enum rtfs_param {
      * SRU slabs = [acc 2][K piece 4][TMEM lane 128][4] with lanes (candidate | reset) and (forget | highway) */
     RTFS_P_RF_FUSED, RTFS_P_RT_FUSED,
     RTFS_P_ENC_WI3, /* encoder conv, 3xTF32 split: image of [W_hi | W_hi | W_lo] (K = 96) */
+    RTFS_P_AT_WQKVI, RTFS_P_AT_WOI, /* tcgen05 images of the attention conv weights: [16][96][4], [16][64][4] */
     RTFS_P_COUNT
 };
 

@@ -71,7 +71,7 @@ P = {n: i for i, n in enumerate(PARAM_NAMES)}
 WS = {n: i for i, n in enumerate(WS_NAMES)}
 ST = {n: i for i, n in enumerate(STAT_NAMES)}
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 _lib = None
 
 

@@ -7,6 +7,7 @@
 
 #include "../../include/rtfs_b200.h"
 #include "attention.cuh"
+#include "att_tc.cuh"
 #include "caf.cuh"
 #include "dprnn.cuh"
 #include "dprnn_fused.cuh"
@@ -413,7 +414,26 @@ int run_mhsa(const Ctx& c, const float* g_in, float* g_out) {
     ra.B = d.B;
     ra.Tc = d.Tc;
     ra.H = H;
-    {
+    const bool att_tc = use_tc() && !env_flag("RTFS_LEGACY_ATT");  // tcgen05 conv + PReLU + LN kernels (att_tc.cuh)
+    if (att_tc) {
+        AttConvArgs aa;
+        memset(&aa, 0, sizeof(aa));
+        aa.x = g_in;
+        aa.wimg = c.P[RTFS_P_AT_WQKVI];
+        aa.bias = ra.bias;
+        aa.slope = ra.slope;
+        aa.gamma = ra.gamma;
+        aa.beta = ra.beta;
+        aa.q = ra.q;
+        aa.k = ra.k;
+        aa.v = ra.v;
+        aa.B = d.B;
+        aa.Tc = d.Tc;
+        aa.H = H;
+        aa.nframes = d.B * d.Tc;
+        STAGE(RTFS_SG_ATT_QKV);
+        CK((launch_att_conv_tc<96, 0>(aa, c.st)));
+    } else {
         static bool cfg = false;
         const int smem = rowblock_smem_floats<96>() * 4;
         if (!cfg) {
@@ -445,7 +465,24 @@ int run_mhsa(const Ctx& c, const float* g_in, float* g_out) {
         attn_core_kernel<<<dim3((d.Tc + AT_QT - 1) / AT_QT, d.B * H), 256, smem, c.st>>>(aa);
         CK(cudaGetLastError());
     }
-    {
+    if (att_tc) {
+        AttConvArgs ab;
+        memset(&ab, 0, sizeof(ab));
+        ab.x = c.buf(RTFS_WS_AO);
+        ab.resid = g_in;
+        ab.wimg = c.P[RTFS_P_AT_WOI];
+        ab.bias = c.P[RTFS_P_AT_BO];
+        ab.slope = c.P[RTFS_P_AT_SLOPEO];
+        ab.gamma = c.P[RTFS_P_AT_GAMMAO];
+        ab.beta = c.P[RTFS_P_AT_BETAO];
+        ab.out = g_out;
+        ab.B = d.B;
+        ab.Tc = d.Tc;
+        ab.H = H;
+        ab.nframes = d.B * d.Tc;
+        STAGE(RTFS_SG_ATT_PROJ);
+        CK((launch_att_conv_tc<64, 1>(ab, c.st)));
+    } else {
         RowblockArgs rb;
         memset(&rb, 0, sizeof(rb));
         rb.x = c.buf(RTFS_WS_AO);

@@ -174,6 +174,8 @@ def prepare(sd, device):
     out["RTFS_P_MK_B"] = g("mask_generator.mask_generator.1.full_layer.2.bias")[perm].contiguous()
     out["RTFS_P_DEC_W"] = g("decoder.decoder.weight").permute(1, 2, 3, 0).reshape(18, 256).contiguous()
 
+    out["RTFS_P_AT_WQKVI"] = umma_image(out["RTFS_P_AT_WQKV"])
+    out["RTFS_P_AT_WOI"] = umma_image(out["RTFS_P_AT_WO"])
     enc_hi = tf32_round(out["RTFS_P_ENC_W"])
     enc_lo = tf32_round(out["RTFS_P_ENC_W"] - enc_hi)
     out["RTFS_P_ENC_WI3"] = umma_image(torch.cat([enc_hi, enc_hi, enc_lo], 1))
