@@ -452,7 +452,7 @@ int run_mhsa(const Ctx& c, const float* g_in, float* g_out) {
         aa.o = c.buf(RTFS_WS_AO);
         aa.Tc = d.Tc;
         aa.H = H;
-        aa.tk_pad = ((d.Tc + 63) / 64) * 64;
+        aa.tk_pad = ((d.Tc + AT_KR - 1) / AT_KR) * AT_KR;
         aa.scale = 1.f / sqrtf(4.f * 64.f);
         const int smem = attn_smem_floats(aa.tk_pad) * 4;
         if (smem > 227 * 1024) return fail_msg("attention: too many frames for the shared-memory score tile");

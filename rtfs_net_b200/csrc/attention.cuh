@@ -159,15 +159,17 @@ struct AttnArgs {
     float scale;        // 1/sqrt(E*F)
 };
 
-constexpr int AT_QT = 32, AT_LDQ = 260, AT_LDV = 136;
-inline int attn_smem_floats(int tk_pad) { return AT_QT * AT_LDQ + AT_QT * (tk_pad + 4) + 64 * AT_LDQ; }
+constexpr int AT_QT = 32, AT_KR = 32, AT_LDQ = 260, AT_LDV = 136;
+// Q tile + score tile + one K/V chunk of AT_KR keys: 83 KB at 125 frames -> two CTAs per SM overlap each other's
+// load -> wait -> MMA rounds
+inline int attn_smem_floats(int tk_pad) { return AT_QT * AT_LDQ + AT_QT * (tk_pad + 4) + AT_KR * AT_LDQ; }
 
-__global__ void __launch_bounds__(256) attn_core_kernel(AttnArgs a) {
+__global__ void __launch_bounds__(256, 2) attn_core_kernel(AttnArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int SLD = a.tk_pad + 4;
     float* Qs = sm;                    // [32][260]
     float* Ss = Qs + AT_QT * AT_LDQ;   // [32][SLD]
-    float* KV = Ss + AT_QT * SLD;      // K chunk [64][260]  /  V chunk [64][136]
+    float* KV = Ss + AT_QT * SLD;      // K chunk [32][260]  /  V chunk [32][136]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int wm = warp & 1, wn = warp >> 1;
     const int bh = blockIdx.y, q0 = blockIdx.x * AT_QT;
@@ -182,21 +184,19 @@ __global__ void __launch_bounds__(256) attn_core_kernel(AttnArgs a) {
         cp_async16(Qs + r * AT_LDQ + c4 * 4, Qg + (long long)(valid ? q0 + r : 0) * 256 + c4 * 4, valid);
     }
     cp_async_commit();
-    const int nkc = a.tk_pad / 64;
-    // ---- S = scale * Q K^T
+    const int nkc = a.tk_pad / AT_KR;
+    // ---- S = scale * Q K^T : warp (wm, wn) -> 16 queries x 8 keys of the chunk
     for (int kc = 0; kc < nkc; ++kc) {
-        for (int i = tid; i < 64 * 64; i += 256) {
+        for (int i = tid; i < AT_KR * 64; i += 256) {
             const int r = i >> 6, c4 = i & 63;
-            const int key = kc * 64 + r;
+            const int key = kc * AT_KR + r;
             const bool valid = key < Tc;
             cp_async16(KV + r * AT_LDQ + c4 * 4, Kg + (long long)(valid ? key : 0) * 256 + c4 * 4, valid);
         }
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();
-        float acc[2][4];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 8
         for (int ks = 0; ks < 32; ++ks) {
             uint32_t af[4];
@@ -205,20 +205,16 @@ __global__ void __launch_bounds__(256) attn_core_kernel(AttnArgs a) {
             af[1] = __float_as_uint(p[8 * AT_LDQ]);
             af[2] = __float_as_uint(p[4]);
             af[3] = __float_as_uint(p[8 * AT_LDQ + 4]);
-#pragma unroll
-            for (int ni = 0; ni < 2; ++ni) {
-                const float* q = KV + (wn * 16 + ni * 8 + g) * AT_LDQ + ks * 8 + t;
-                uint32_t bf[2] = {__float_as_uint(q[0]), __float_as_uint(q[4])};
-                mma_tf32(acc[ni], af, bf);
-            }
+            const float* q = KV + (wn * 8 + g) * AT_LDQ + ks * 8 + t;
+            uint32_t bf[2] = {__float_as_uint(q[0]), __float_as_uint(q[4])};
+            mma_tf32(acc, af, bf);
         }
-#pragma unroll
-        for (int ni = 0; ni < 2; ++ni) {
-            const int r = wm * 16 + g, col = kc * 64 + wn * 16 + ni * 8 + 2 * t;
-            Ss[r * SLD + col] = acc[ni][0] * a.scale;
-            Ss[r * SLD + col + 1] = acc[ni][1] * a.scale;
-            Ss[(r + 8) * SLD + col] = acc[ni][2] * a.scale;
-            Ss[(r + 8) * SLD + col + 1] = acc[ni][3] * a.scale;
+        {
+            const int r = wm * 16 + g, col = kc * AT_KR + wn * 8 + 2 * t;
+            Ss[r * SLD + col] = acc[0] * a.scale;
+            Ss[r * SLD + col + 1] = acc[1] * a.scale;
+            Ss[(r + 8) * SLD + col] = acc[2] * a.scale;
+            Ss[(r + 8) * SLD + col + 1] = acc[3] * a.scale;
         }
         __syncthreads();
     }
@@ -239,16 +235,16 @@ __global__ void __launch_bounds__(256) attn_core_kernel(AttnArgs a) {
         for (int j = lane; j < a.tk_pad; j += 32) row[j] = j < Tc ? tf32r(row[j] * inv) : 0.f;
     }
     __syncthreads();
-    // ---- O = P V, 128 value columns at a time
+    // ---- O = P V, 128 value columns at a time: warp (wm, wn) -> 16 queries x 32 columns
     const int b = bh / a.H, h = bh - b * a.H;
     for (int nc = 0; nc < 8; ++nc) {
         float acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
         for (int kc = 0; kc < nkc; ++kc) {
-            for (int i = tid; i < 64 * 32; i += 256) {
+            for (int i = tid; i < AT_KR * 32; i += 256) {
                 const int r = i >> 5, c4 = i & 31;
-                const int key = kc * 64 + r;
+                const int key = kc * AT_KR + r;
                 const bool valid = key < Tc;
                 cp_async16(KV + r * AT_LDV + c4 * 4, Vg + (long long)(valid ? key : 0) * 1024 + nc * 128 + c4 * 4, valid);
             }
@@ -256,9 +252,9 @@ __global__ void __launch_bounds__(256) attn_core_kernel(AttnArgs a) {
             cp_async_wait<0>();
             __syncthreads();
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
+            for (int ks = 0; ks < AT_KR / 8; ++ks) {
                 uint32_t af[4];
-                const float* p = Ss + (wm * 16 + g) * SLD + kc * 64 + ks * 8 + t;
+                const float* p = Ss + (wm * 16 + g) * SLD + kc * AT_KR + ks * 8 + t;
                 af[0] = __float_as_uint(p[0]);
                 af[1] = __float_as_uint(p[8 * SLD]);
                 af[2] = __float_as_uint(p[4]);
