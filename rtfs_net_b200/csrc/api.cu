@@ -40,12 +40,12 @@ bool use_fused_dprnn() {  // RTFS_UNFUSED_DPRNN=1: prep + GEMM + scan kernels in
     return v;
 }
 // Which full-resolution 1x1 convs run the persistent warp-specialised kernel (gemm_tcp.cuh) instead of the
-// one-tile-per-CTA kernel (gemm_tc.cuh): bit 0 bottleneck, 1 gate+projection, 2 residual conv, 3 mask.
+// one-tile-per-CTA kernel (gemm_tc.cuh): bit 0 bottleneck, 1 gate+projection, 2 residual conv, 3 mask (default 11: all but the residual conv).
 // RTFS_PERSIST_MASK overrides (A/B measurement).
 bool use_persistent(int bit) {
     static const int mask = [] {
         const char* v = getenv("RTFS_PERSIST_MASK");
-        return v ? atoi(v) : 9;
+        return v ? atoi(v) : 11;
     }();
     return (mask >> bit) & 1;
 }

@@ -123,20 +123,26 @@ struct GateLoader {
     const float* bg;
     const float* slope;  // 1 float
     int C;
-    static constexpr int kExtra = 0;
+    // the 2 x 256 gateway coefficients live in shared memory: with ~200 KB of the SM's L1/shared array carved out for
+    // shared memory the streaming A loads evict them from L1, and a global re-load would sit in every chunk's dependent chain
+    static constexpr int kExtra = 512;
+    static constexpr bool kTileInvariant = true;  // the table does not depend on the tile: a persistent kernel fills it once
     int row0_, M_, rs_;
     float a_;
-    DEVINL void init(int row0, int M, float*) {
-        row0_ = row0 + (threadIdx.x >> 3);
-        rs_ = blockDim.x >> 3;
-        M_ = M;
-        a_ = __ldg(slope);
-    }
-    DEVINL void init_p(int row0, int M, float*, int ptid, int nthr) {
+    const float* tab_;
+    DEVINL void init(int row0, int M, float* extra) { init_p(row0, M, extra, threadIdx.x, blockDim.x); }
+    DEVINL void init_p(int row0, int M, float* extra, int ptid, int nthr) {
         row0_ = row0 + (ptid >> 3);
         rs_ = nthr >> 3;
         M_ = M;
         a_ = __ldg(slope);
+        tab_ = extra;
+        for (int i = ptid; i < 128; i += nthr) {
+            const float4 w = ldg4(wg + 4 * (i & 63));
+            const float4 bb = ldg4(bg + 4 * (i & 63));
+            if (i < 64) *reinterpret_cast<float4*>(extra + 4 * i) = w;
+            else *reinterpret_cast<float4*>(extra + 4 * i) = bb;
+        }
     }
     DEVINL float4 load(int i, int k) const {
         const int row = row0_ + rs_ * i;
@@ -145,7 +151,7 @@ struct GateLoader {
     }
     DEVINL const float* raw(long long row, int k) const { return A + row * C + k; }
     DEVINL float4 xform(float4 x, int, int k) const {
-        const float4 w = ldg4(wg + k), b = ldg4(bg + k);
+        const float4 w = *reinterpret_cast<const float4*>(tab_ + k), b = *reinterpret_cast<const float4*>(tab_ + 256 + k);
         float4 y;
         y.x = prelu(fmaf(w.x, x.x, b.x), a_);
         y.y = prelu(fmaf(w.y, x.y, b.y), a_);

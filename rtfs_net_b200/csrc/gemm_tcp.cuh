@@ -19,6 +19,15 @@
 
 namespace rtfs {
 
+template <class AL, class = void>
+struct loader_tile_invariant {
+    static constexpr bool value = false;
+};
+template <class AL>
+struct loader_tile_invariant<AL, decltype((void)AL::kTileInvariant)> {
+    static constexpr bool value = AL::kTileInvariant;
+};
+
 constexpr int TCP_EPI = 256;  // epilogue threads (warps 0-7); then NPROD producer threads, the MMA warp and the weight warp
 
 DEVINL void mbar_arrive_cta(uint64_t* bar) {
@@ -213,8 +222,8 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
                     if (g >= G) break;
                     const int it = g / NK, kc = g - it * NK;
                     const int row0 = (blockIdx.x + it * gridDim.x) * TC_BM;
-                    if (kc == 0) {
-                        al.init_p(row0, M, extra + (it & 1) * AL::kExtra, ptid, TCP_PROD);
+                    if (kc == 0 && (!loader_tile_invariant<AL>::value || it == 0)) {
+                        al.init_p(row0, M, extra + (loader_tile_invariant<AL>::value ? 0 : (it & 1)) * AL::kExtra, ptid, TCP_PROD);
                         if (AL::kExtra > 0) named_bar_sync(2, TCP_PROD);
                     }
                     const int s = g % NSA;
