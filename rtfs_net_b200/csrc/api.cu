@@ -49,8 +49,9 @@ bool use_persistent(int bit) {
     }();
     return (mask >> bit) & 1;
 }
-bool use_wide() {  // RTFS_NARROW_GEMM=1: 256-thread CTAs for gate+projection / residual conv (default 512: more loading warps)
-    static const bool v = !env_flag("RTFS_NARROW_GEMM");
+bool use_wide() {  // RTFS_WIDE_GEMM=1: 512-thread CTAs for the residual conv (64 registers/thread: spills; measured slower since the
+                   // epilogue constants are cached per column block)
+    static const bool v = env_flag("RTFS_WIDE_GEMM");
     return v;
 }
 bool use_unfold() {  // RTFS_NO_UNFOLD=1: overlapping-view GEMMs through the generic im2col-style loader
@@ -690,7 +691,7 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out, boo
             ResidOutCafEpi4 ep{out, P[RTFS_P_RC_B], x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], addend,
                                c.buf(RTFS_WS_VK), c.buf(RTFS_WS_ATT), P[RTFS_P_CAF_SK], P[RTFS_P_CAF_TK], P[RTFS_P_CAF_SV], P[RTFS_P_CAF_TV],
                                d.T, d.F, d.Tv, 0.f};
-            CK((launch_gemm_tc<256, 64, 2, 2, 2, 512>(al, P[RTFS_P_RC_WI], ep, M, c.st)));
+            CK((launch_gemm_tc<256, 64, 2, 2, 2, 256>(al, P[RTFS_P_RC_WI], ep, M, c.st)));
         } else if (use_tc()) {
             ResidOutEpi4 ep{out, P[RTFS_P_RC_B], x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], addend, 0.f};
             if (use_persistent(2)) CK((launch_gemm_tcp<256, 64, 4, 1, true, 2, 0, 256>(al, P[RTFS_P_RC_WI], ep, M, c.st)));

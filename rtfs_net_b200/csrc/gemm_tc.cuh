@@ -150,6 +150,7 @@ struct StoreEpi4 {
     const float* bias;  // may be null
     using Pre = NoPre;
     DEVINL void init(int, int) {}
+    DEVINL void prep(int) {}
     DEVINL Pre load(int, int) const { return Pre{}; }
     DEVINL void store4(int row, int col, float4 v, const Pre&) {
         if (bias) v = add4(v, ldg4(bias + col));
@@ -173,6 +174,7 @@ struct StatsEpi4 {
         s0_ = q0_ = s1_ = q1_ = 0.f;
     }
     using Pre = NoPre;
+    DEVINL void prep(int) {}
     DEVINL Pre load(int, int) const { return Pre{}; }
     DEVINL void store4(int row, int col, float4 v, const Pre&) {
         if (bias) v = add4(v, ldg4(bias + col));
@@ -210,7 +212,13 @@ struct ResidOutEpi4 {
     struct Pre {
         float4 x, a1;
     };
+    float4 w_, b_, bi_;  // per-column constants of the current 32-column block (prep)
     DEVINL void init(int, int) { a_ = __ldg(slope); }
+    DEVINL void prep(int col) {
+        w_ = ldg4(wg + col);
+        b_ = ldg4(bg + col);
+        bi_ = ldg4(bias + col);
+    }
     DEVINL Pre load(int row, int col) const {
         const long long o = (long long)row * 256 + col;
         Pre p;
@@ -220,7 +228,7 @@ struct ResidOutEpi4 {
     }
     DEVINL void store4(int row, int col, float4 v, const Pre& p) {
         const long long o = (long long)row * 256 + col;
-        const float4 w = ldg4(wg + col), b = ldg4(bg + col), bi = ldg4(bias + col);
+        const float4 w = w_, b = b_, bi = bi_;
         v.x += bi.x + prelu(fmaf(w.x, p.x.x, b.x), a_) + p.a1.x;
         v.y += bi.y + prelu(fmaf(w.y, p.x.y, b.y), a_) + p.a1.y;
         v.z += bi.z + prelu(fmaf(w.z, p.x.z, b.z), a_) + p.a1.z;
@@ -253,7 +261,17 @@ struct ResidOutCafEpi4 {
     struct Pre {
         float4 x, a1;
     };
+    float4 w_, b_, bi_, s1_, t1_, s2_, t2_;  // per-column constants of the current 32-column block
     DEVINL void init(int, int) { a_ = __ldg(slope); }
+    DEVINL void prep(int col) {
+        w_ = ldg4(wg + col);
+        b_ = ldg4(bg + col);
+        bi_ = ldg4(bias + col);
+        s1_ = ldg4(sk + col);
+        t1_ = ldg4(tk + col);
+        s2_ = ldg4(sv + col);
+        t2_ = ldg4(tv + col);
+    }
     DEVINL Pre load(int row, int col) const {
         const long long o = (long long)row * 256 + col;
         Pre p;
@@ -263,7 +281,7 @@ struct ResidOutCafEpi4 {
     }
     DEVINL void store4(int row, int col, float4 v, const Pre& p) {
         const long long o = (long long)row * 256 + col;
-        const float4 w = ldg4(wg + col), b = ldg4(bg + col), bi = ldg4(bias + col);
+        const float4 w = w_, b = b_, bi = bi_;
         v.x += bi.x + prelu(fmaf(w.x, p.x.x, b.x), a_);
         v.y += bi.y + prelu(fmaf(w.y, p.x.y, b.y), a_);
         v.z += bi.z + prelu(fmaf(w.z, p.x.z, b.z), a_);
@@ -272,7 +290,7 @@ struct ResidOutCafEpi4 {
         const int tvi = (t * Tv) / T;  // nearest: floor(t * Tv / T) (< Tv)
         const long long vo = ((long long)bb * Tv + tvi) * 256 + col;
         const float4 k = ldg4(vk + vo), at = ldg4(att + vo);
-        const float4 s1 = ldg4(sk + col), t1 = ldg4(tk + col), s2 = ldg4(sv + col), t2 = ldg4(tv + col);
+        const float4 s1 = s1_, t1 = t1_, s2 = s2_, t2 = t2_;
         float4 y;
         y.x = fmaxf(fmaf(v.x, s1.x, t1.x), 0.f) * k.x + at.x * fmaf(v.x, s2.x, t2.x) + p.a1.x;
         y.y = fmaxf(fmaf(v.y, s1.y, t1.y), 0.f) * k.y + at.y * fmaf(v.y, s2.y, t2.y) + p.a1.y;
@@ -294,6 +312,7 @@ struct MaskEpi4 {
         float2 er, ei;
     };
     DEVINL void init(int, int) {}
+    DEVINL void prep(int) {}
     DEVINL Pre load(int row, int col) const {
         const long long o = (long long)row * 256 + (col >> 1);
         Pre p;
@@ -325,6 +344,7 @@ struct ConvTEpi4 {
         long long off;  // < 0: padding row, nothing to store
     };
     DEVINL void init(int, int) {}
+    DEVINL void prep(int) {}
     DEVINL Pre load(int row, int col) const {
         Pre p;
         const int seq = row / (S + 7), s = row - seq * (S + 7);
@@ -490,6 +510,7 @@ __global__ void __launch_bounds__(NT, MINB) gemm_tc_kernel(AL al, const float* _
             const int col0 = hlf * (BN / NCG) + cb * 32;
             // all global loads of this 32x32 block are issued first and stay in flight while the
             // accumulator block is read from TMEM and transposed through shared memory
+            ep.prep(col0 + c4);
             typename EP::Pre pre[8];
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
@@ -624,6 +645,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) gemm_tc_unfold_kernel(const 
             const int col0 = hlf * (BN / 2) + cb * 32;
             // all global loads of this 32x32 block are issued first and stay in flight while the
             // accumulator block is read from TMEM and transposed through shared memory
+            ep.prep(col0 + c4);
             typename EP::Pre pre[8];
 #pragma unroll
             for (int p = 0; p < 8; ++p) {

@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
                 const int col0 = hlf * (BN / 2) + cb * 32;
                 // all global loads of this 32x32 block are issued first and stay in flight while the
                 // accumulator block is read from TMEM and transposed through shared memory
+                ep.prep(col0 + c4);
                 typename EP::Pre pre[8];
 #pragma unroll
                 for (int p = 0; p < 8; ++p) {
