@@ -149,11 +149,12 @@ struct StoreEpi4 {
     long long ldc;
     const float* bias;  // may be null
     using Pre = NoPre;
+    float4 bi_;
     DEVINL void init(int, int) {}
-    DEVINL void prep(int) {}
+    DEVINL void prep(int col) { bi_ = bias ? ldg4(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f); }
     DEVINL Pre load(int, int) const { return Pre{}; }
     DEVINL void store4(int row, int col, float4 v, const Pre&) {
-        if (bias) v = add4(v, ldg4(bias + col));
+        v = add4(v, bi_);
         *reinterpret_cast<float4*>(C + (long long)row * ldc + col) = v;
     }
     DEVINL void finish(float*) {}
@@ -174,10 +175,11 @@ struct StatsEpi4 {
         s0_ = q0_ = s1_ = q1_ = 0.f;
     }
     using Pre = NoPre;
-    DEVINL void prep(int) {}
+    float4 bi_;
+    DEVINL void prep(int col) { bi_ = bias ? ldg4(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f); }
     DEVINL Pre load(int, int) const { return Pre{}; }
     DEVINL void store4(int row, int col, float4 v, const Pre&) {
-        if (bias) v = add4(v, ldg4(bias + col));
+        v = add4(v, bi_);
         *reinterpret_cast<float4*>(C + (long long)row * ldc + col) = v;
         const float s = (v.x + v.y) + (v.z + v.w);
         const float q = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
@@ -311,8 +313,9 @@ struct MaskEpi4 {
     struct Pre {
         float2 er, ei;
     };
+    float4 bi_;
     DEVINL void init(int, int) {}
-    DEVINL void prep(int) {}
+    DEVINL void prep(int col) { bi_ = ldg4(bias + col); }
     DEVINL Pre load(int row, int col) const {
         const long long o = (long long)row * 256 + (col >> 1);
         Pre p;
@@ -321,7 +324,7 @@ struct MaskEpi4 {
         return p;
     }
     DEVINL void store4(int row, int col, float4 v, const Pre& p) {
-        const float4 bi = ldg4(bias + col);
+        const float4 bi = bi_;
         const float mr0 = fmaxf(v.x + bi.x, 0.f), mi0 = fmaxf(v.y + bi.y, 0.f);
         const float mr1 = fmaxf(v.z + bi.z, 0.f), mi1 = fmaxf(v.w + bi.w, 0.f);
         const long long o = (long long)row * 256 + (col >> 1);
