@@ -616,7 +616,7 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out, boo
             a.w[0] = P[RTFS_P_C0_EW]; a.out[0] = gec; a.sums[0] = c.stat(RTFS_ST_C0E);
             a.w[1] = P[RTFS_P_C0_GW]; a.out[1] = ggc; a.sums[1] = c.stat(RTFS_ST_C0G);
             STAGE(RTFS_SG_TFAR_CAT_GLOBAL);
-            CK((launch_dwroll<XrTfar, 2, false, 128>(xf, a, d.B, c.st)));
+            CK((launch_dwroll<XrTfar, 2, false, 128, true, 4>(xf, a, d.B, c.st)));
         }
         {
             // f0 = TFAR_fus0(d0, g) formed on the fly -> local conv of concat_layers.0

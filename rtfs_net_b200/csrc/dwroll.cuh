@@ -187,7 +187,7 @@ struct DrArgs {
 };
 
 // NT threads = 8 channel pairs x NT/8 strips of 4 columns  (NT/8 >= ceil(Fi/4))
-template <class XF, int NW, bool DUAL, int NT>
+template <class XF, int NW, bool DUAL, int NT, int NR = DR_NR>
 __global__ void __launch_bounds__(NT, (NT > 256 ? 2 : 4)) dwroll_kernel(XF xf, DrArgs<NW> a) {
     constexpr int NCONV = NW + (DUAL ? 1 : 0);
     extern __shared__ __align__(16) float dr_smem[];
@@ -216,14 +216,14 @@ __global__ void __launch_bounds__(NT, (NT > 256 ? 2 : 4)) dwroll_kernel(XF xf, D
     }
     xf.init(b, cg, pair, active ? f0 : 0);
 
-    // input rows r = t0-1 .. t1+1 ; row r lives in slot (r - (t0-1)) % DR_NR
+    // input rows r = t0-1 .. t1+1 ; row r lives in slot (r - (t0-1)) % NR
     const int r_first = t0 - 1, r_last = t1 + 1;
     auto issue = [&](int r) {
-        if (r >= 0 && r < Ti && r <= r_last) xf.issue(r, dr_smem + ((r - r_first) % DR_NR) * slot_fl, tid, NT);
+        if (r >= 0 && r < Ti && r <= r_last) xf.issue(r, dr_smem + ((r - r_first) % NR) * slot_fl, tid, NT);
         cp_async_commit();
     };
 #pragma unroll
-    for (int i = 0; i < DR_NR - 1; ++i) issue(r_first + i);
+    for (int i = 0; i < NR - 1; ++i) issue(r_first + i);
 
     // win[slot][q]: 4 input rows x 7 columns (f0-1 .. f0+5).  The row loop is unrolled by 4 so that the slot a new
     // row lands in (step & 3) and the logical window order are compile-time: no register moves when the window rolls.
@@ -245,11 +245,11 @@ __global__ void __launch_bounds__(NT, (NT > 256 ? 2 : 4)) dwroll_kernel(XF xf, D
         for (int k = 0; k < 4; ++k) {
             const int r = rb + k;
             if (r > r_last) break;       // uniform over the CTA
-            cp_async_wait<DR_NR - 2>();  // this thread's pieces of row r have landed
+            cp_async_wait<NR - 2>();  // this thread's pieces of row r have landed
             __syncthreads();             // everyone's have; everyone is done reading row r-1's slot
-            issue(r + DR_NR - 1);        // -> into the slot of row r-1
+            issue(r + NR - 1);        // -> into the slot of row r-1
             const bool rvalid = r >= 0 && r < Ti;
-            const float* slot = dr_smem + ((r - r_first) % DR_NR) * slot_fl;
+            const float* slot = dr_smem + ((r - r_first) % NR) * slot_fl;
 #pragma unroll
             for (int q = 0; q < 7; ++q) {
                 const int f = f0 - 1 + q;
@@ -488,10 +488,12 @@ inline int dr_rows_per_seg(int T, int B, int ctas_per_sm) {
     return best;
 }
 
-template <class XF, int NW, bool DUAL, int NT, bool PACKED = true>
+// NR: ring slots (rows in flight + 1); the compressed-resolution instances use 4 so that 4 CTAs fit an SM
+template <class XF, int NW, bool DUAL, int NT, bool PACKED = true, int NR = DR_NR>
 inline cudaError_t launch_dwroll(const XF& xf, DrArgs<NW> a, int B, cudaStream_t st) {
-    auto kern = PACKED ? dwroll_kernel<XF, NW, DUAL, NT> : dwroll_scalar_kernel<XF, NW, DUAL, NT>;
-    const int smem = DR_NR * xf.slot_floats() * 4;
+    static_assert(PACKED || NR == DR_NR, "the scalar kernel uses the default ring depth");
+    auto kern = PACKED ? dwroll_kernel<XF, NW, DUAL, NT, NR> : dwroll_scalar_kernel<XF, NW, DUAL, NT>;
+    const int smem = NR * xf.slot_floats() * 4;
     static int configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
