@@ -688,6 +688,7 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out, boo
         al.B = d.B;
         STAGE(RTFS_SG_RESID_OUT);
         if (caf_fused) {
+            if (addend != nullptr && addend != x) return -2;  // fused pass: the addend is the block input itself
             ResidOutCafEpi4 ep{out, P[RTFS_P_RC_B], x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], addend,
                                c.buf(RTFS_WS_VK), c.buf(RTFS_WS_ATT), P[RTFS_P_CAF_SK], P[RTFS_P_CAF_TK], P[RTFS_P_CAF_SV], P[RTFS_P_CAF_TV],
                                d.T, d.F, d.Tv, 0.f};
@@ -888,7 +889,7 @@ int rtfs_avnet_forward(const float* const* params, const float* wav, const float
     RUN(run_bottleneck(c, a0, a1, false));
     // refinement_module.py:45-62 with fusion_repeats = 1
     float *cur = xb, *other = xa;
-    if (use_tc() && !env_flag("RTFS_UNFUSED_CAF")) {
+    if (use_tc() && !env_flag("RTFS_UNFUSED_CAF") && c.d.F >= 32) {  // the fused epilogue assumes <= 2 frames per 32 rows
         RUN(run_caf_video(c, video));
         RUN(run_block(c, a1, repeats > 1 ? a1 : nullptr, xb, true));
     } else {

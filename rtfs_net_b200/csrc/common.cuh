@@ -82,7 +82,7 @@ DEVINL void gln_mean_rstd(const double* __restrict__ sums, int b, double inv_n, 
     double var = ss * inv_n - m * m;
     var = var < 0.0 ? 0.0 : var;
     mean = (float)m;
-    rstd = (float)(1.0 / sqrt(var + 1e-5));
+    rstd = (float)rsqrt(var + 1e-5);
 }
 
 // A gLN to be applied on load: y = x * sc[c] + sh[c] with sc = rstd*gamma, sh = beta - mean*rstd*gamma
@@ -99,6 +99,11 @@ DEVINL float sigmoidf_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); 
 // F.interpolate(mode='nearest'): src = min(floor(dst*in/out), in-1)
 DEVINL int nearest_src(int dst, int n_in, int n_out) {
     int s = (int)(((long long)dst * n_in) / n_out);
+    return s < n_in - 1 ? s : n_in - 1;
+}
+// same, 32-bit arithmetic: exact while dst * n_in < 2^32 (every (T, F) this library accepts: both < 65536)
+DEVINL int nearest_src32(int dst, int n_in, int n_out) {
+    const int s = (int)(((unsigned)dst * (unsigned)n_in) / (unsigned)n_out);
     return s < n_in - 1 ? s : n_in - 1;
 }
 

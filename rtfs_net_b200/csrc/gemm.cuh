@@ -207,18 +207,38 @@ struct TfarLoader {
     GlnRef n_l, n_d, n_g, n_e;
     int T, F, Tc, Fc, B;
     static constexpr int kExtra = 4 * 4 * 64;  // 4 norms x [2][64][2]
+    static constexpr bool kBatched = true;     // raw_load / xform_raw: the tcgen05 kernels issue a chunk's loads as one batch
     int row0_, M_, rs_, bfirst_, P_;
     const float* tab_;
     long long offc_[4];
     int s_[4];
+    struct Raw {
+        float4 l, d, g, e;
+    };
     DEVINL void init(int row0, int M, float* extra) { init_p(row0, M, extra, threadIdx.x, blockDim.x); }
     DEVINL void init_p(int row0, int M, float* extra, int ptid, int nthr) {
         P_ = T * F;
         bfirst_ = row0 / P_;
-        fill_gln_table(extra, n_l, bfirst_, B, 64, ptid, nthr);
-        fill_gln_table(extra + 256, n_d, bfirst_, B, 64, ptid, nthr);
-        fill_gln_table(extra + 512, n_g, bfirst_, B, 64, ptid, nthr);
-        fill_gln_table(extra + 768, n_e, bfirst_, B, 64, ptid, nthr);
+        // the four scale/shift tables in one pass: entry i = (norm i>>7, sample (i>>6)&1, channel i&63); the loads of
+        // all of a thread's entries are independent, so the fill costs one L2 round trip instead of one per table
+#pragma unroll 2
+        for (int i = ptid; i < 512; i += nthr) {
+            const int nb = i >> 7, s = (i >> 6) & 1, c = i & 63;
+            // selects on the fields (a reference select would spill the four structs to local memory)
+            const double* sums = nb == 0 ? n_l.sums : nb == 1 ? n_d.sums : nb == 2 ? n_g.sums : n_e.sums;
+            const float* gamma = nb == 0 ? n_l.gamma : nb == 1 ? n_d.gamma : nb == 2 ? n_g.gamma : n_e.gamma;
+            const float* beta = nb == 0 ? n_l.beta : nb == 1 ? n_d.beta : nb == 2 ? n_g.beta : n_e.beta;
+            const double inv_n = nb == 0 ? n_l.inv_n : nb == 1 ? n_d.inv_n : nb == 2 ? n_g.inv_n : n_e.inv_n;
+            const int b = bfirst_ + s;
+            float sc = 0.f, sh = 0.f;
+            if (b < B) {
+                float mean, rstd;
+                gln_mean_rstd(sums, b, inv_n, mean, rstd);
+                sc = rstd * __ldg(gamma + c);
+                sh = __ldg(beta + c) - mean * sc;
+            }
+            *reinterpret_cast<float2*>(extra + 2 * i) = make_float2(sc, sh);
+        }
         tab_ = extra;
         row0_ = row0 + (ptid >> 3);
         rs_ = nthr >> 3;
@@ -230,7 +250,7 @@ struct TfarLoader {
             const int b = row / P_;
             const int p = row - b * P_;
             const int t = p / F, f = p - t * F;
-            const int tc = nearest_src(t, Tc, T), fc = nearest_src(f, Fc, F);
+            const int tc = nearest_src32(t, Tc, T), fc = nearest_src32(f, Fc, F);
             offc_[i] = (((long long)b * Tc + tc) * Fc + fc) * 64;
             s_[i] = b - bfirst_;
         }
@@ -239,21 +259,28 @@ struct TfarLoader {
         const float* tb = tab + 2 * (s * 64 + k);
         return fmaf(x, tb[0], tb[1]);
     }
-    DEVINL float4 load(int i, int k) const {
-        const int row = row0_ + rs_ * i;
-        if (row >= M_) return make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 xl = ldg4(lec + (long long)row * 64 + k);
-        const float4 xd = ldg4(d0 + (long long)row * 64 + k);
-        const float4 xg = ldg4(ggc + offc_[i] + k);
-        const float4 xe = ldg4(gec + offc_[i] + k);
+    // the four operand loads of row i (clamped to the last valid row: xform_raw zeroes rows past M)
+    DEVINL Raw raw_load(int i, int k) const {
+        int row = row0_ + rs_ * i;
+        row = row < M_ ? row : M_ - 1;
+        Raw r;
+        r.l = ldg4(lec + (long long)row * 64 + k);
+        r.d = ldg4(d0 + (long long)row * 64 + k);
+        r.g = ldg4(ggc + offc_[i] + k);
+        r.e = ldg4(gec + offc_[i] + k);
+        return r;
+    }
+    DEVINL float4 xform_raw(const Raw& r, int i, int k) const {
+        if (row0_ + rs_ * i >= M_) return make_float4(0.f, 0.f, 0.f, 0.f);
         const int s = s_[i];
         float4 y;
-        y.x = nrm(tab_, s, k, xl.x) * sigmoidf_fast(nrm(tab_ + 512, s, k, xg.x)) + nrm(tab_ + 768, s, k, xe.x) + nrm(tab_ + 256, s, k, xd.x);
-        y.y = nrm(tab_, s, k + 1, xl.y) * sigmoidf_fast(nrm(tab_ + 512, s, k + 1, xg.y)) + nrm(tab_ + 768, s, k + 1, xe.y) + nrm(tab_ + 256, s, k + 1, xd.y);
-        y.z = nrm(tab_, s, k + 2, xl.z) * sigmoidf_fast(nrm(tab_ + 512, s, k + 2, xg.z)) + nrm(tab_ + 768, s, k + 2, xe.z) + nrm(tab_ + 256, s, k + 2, xd.z);
-        y.w = nrm(tab_, s, k + 3, xl.w) * sigmoidf_fast(nrm(tab_ + 512, s, k + 3, xg.w)) + nrm(tab_ + 768, s, k + 3, xe.w) + nrm(tab_ + 256, s, k + 3, xd.w);
+        y.x = nrm(tab_, s, k, r.l.x) * sigmoidf_fast(nrm(tab_ + 512, s, k, r.g.x)) + nrm(tab_ + 768, s, k, r.e.x) + nrm(tab_ + 256, s, k, r.d.x);
+        y.y = nrm(tab_, s, k + 1, r.l.y) * sigmoidf_fast(nrm(tab_ + 512, s, k + 1, r.g.y)) + nrm(tab_ + 768, s, k + 1, r.e.y) + nrm(tab_ + 256, s, k + 1, r.d.y);
+        y.z = nrm(tab_, s, k + 2, r.l.z) * sigmoidf_fast(nrm(tab_ + 512, s, k + 2, r.g.z)) + nrm(tab_ + 768, s, k + 2, r.e.z) + nrm(tab_ + 256, s, k + 2, r.d.z);
+        y.w = nrm(tab_, s, k + 3, r.l.w) * sigmoidf_fast(nrm(tab_ + 512, s, k + 3, r.g.w)) + nrm(tab_ + 768, s, k + 3, r.e.w) + nrm(tab_ + 256, s, k + 3, r.d.w);
         return y;
     }
+    DEVINL float4 load(int i, int k) const { return xform_raw(raw_load(i, k), i, k); }
 };
 
 // im2col of the 2-channel spectrogram for the 3x3 encoder conv (encoder.py:147-173):

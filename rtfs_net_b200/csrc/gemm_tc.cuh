@@ -237,6 +237,32 @@ struct ResidOutEpi4 {
         v.w += bi.w + prelu(fmaf(w.w, p.x.w, b.w), a_) + p.a1.w;
         *reinterpret_cast<float4*>(out + o) = v;
     }
+    // affine variant used by gemm_tc_kernel: the eight rows a thread touches in a 32x32 block are rowq0 + rsub + 4p, so
+    // every access is one of three block pointers plus a compile-time offset (no per-access 64-bit address arithmetic)
+    static constexpr bool kAffine = true;
+    const float *xp_, *a1p_;
+    float* op_;
+    DEVINL void prep_block(int rowq0, int rsub, int col, int) {
+        prep(col);
+        const long long o = (long long)(rowq0 + rsub) * 256 + col;
+        xp_ = x + o;
+        a1p_ = a1 ? a1 + o : nullptr;
+        op_ = out + o;
+    }
+    DEVINL Pre load_p(int p) const {
+        Pre r;
+        r.x = ldg4(xp_ + p * 1024);
+        r.a1 = a1p_ ? ldg4(a1p_ + p * 1024) : make_float4(0.f, 0.f, 0.f, 0.f);
+        return r;
+    }
+    DEVINL void store_p(int p, int, float4 v, const Pre& r) {
+        const float4 w = w_, b = b_, bi = bi_;
+        v.x += bi.x + prelu(fmaf(w.x, r.x.x, b.x), a_) + r.a1.x;
+        v.y += bi.y + prelu(fmaf(w.y, r.x.y, b.y), a_) + r.a1.y;
+        v.z += bi.z + prelu(fmaf(w.z, r.x.z, b.z), a_) + r.a1.z;
+        v.w += bi.w + prelu(fmaf(w.w, r.x.w, b.w), a_) + r.a1.w;
+        *reinterpret_cast<float4*>(op_ + p * 1024) = v;
+    }
     DEVINL void finish(float*) {}
     DEVINL void finish_group(float*, int, int, int) {}
 };
@@ -299,6 +325,58 @@ struct ResidOutCafEpi4 {
         y.z = fmaxf(fmaf(v.z, s1.z, t1.z), 0.f) * k.z + at.z * fmaf(v.z, s2.z, t2.z) + p.a1.z;
         y.w = fmaxf(fmaf(v.w, s1.w, t1.w), 0.f) * k.w + at.w * fmaf(v.w, s2.w, t2.w) + p.a1.w;
         *reinterpret_cast<float4*>(out + o) = y;
+    }
+    // affine variant (see ResidOutEpi4).  The 32 rows of a warp's block are consecutive positions, so with F >= 32 they
+    // lie in at most two (b, t) frames: the video key / attention vectors of both frames are loaded once per block
+    // instead of once per row behind the previous row's store (host side falls back to the unfused CAF when F < 32).
+    static constexpr bool kAffine = true;
+    // In the fused pass the addend, when present, IS the block input (a1 + block(a1)): one load serves both.
+    struct PreA {
+        float4 x;
+    };
+    const float* xp_;
+    float* op_;
+    bool addx_;
+    float4 k0_, at0_, k1_, at1_;
+    int rsplit_;  // first row of the second frame
+    DEVINL long long vrow(int bt) const {
+        const int t = bt % T, bb = bt / T;
+        return ((long long)bb * Tv + (t * Tv) / T) * 256;  // nearest: floor(t * Tv / T) (< Tv)
+    }
+    DEVINL void prep_block(int rowq0, int rsub, int col, int M) {
+        prep(col);
+        const long long o = (long long)(rowq0 + rsub) * 256 + col;
+        xp_ = x + o;
+        addx_ = a1 != nullptr;
+        op_ = out + o;
+        const int bt0 = rowq0 / F;
+        rsplit_ = (bt0 + 1) * F;
+        const long long v0 = vrow(bt0) + col, v1 = (rsplit_ < M ? vrow(bt0 + 1) : vrow(bt0)) + col;
+        k0_ = ldg4(vk + v0);
+        at0_ = ldg4(att + v0);
+        k1_ = ldg4(vk + v1);
+        at1_ = ldg4(att + v1);
+    }
+    DEVINL PreA load_p(int p) const {
+        PreA r;
+        r.x = ldg4(xp_ + p * 1024);
+        return r;
+    }
+    DEVINL void store_p(int p, int row, float4 v, const PreA& r) {
+        const float4 w = w_, b = b_, bi = bi_;
+        v.x += bi.x + prelu(fmaf(w.x, r.x.x, b.x), a_);
+        v.y += bi.y + prelu(fmaf(w.y, r.x.y, b.y), a_);
+        v.z += bi.z + prelu(fmaf(w.z, r.x.z, b.z), a_);
+        v.w += bi.w + prelu(fmaf(w.w, r.x.w, b.w), a_);
+        const bool second = row >= rsplit_;
+        const float4 k = second ? k1_ : k0_, at = second ? at1_ : at0_;
+        const float4 s1 = s1_, t1 = t1_, s2 = s2_, t2 = t2_;
+        float4 y;
+        y.x = fmaxf(fmaf(v.x, s1.x, t1.x), 0.f) * k.x + at.x * fmaf(v.x, s2.x, t2.x) + (addx_ ? r.x.x : 0.f);
+        y.y = fmaxf(fmaf(v.y, s1.y, t1.y), 0.f) * k.y + at.y * fmaf(v.y, s2.y, t2.y) + (addx_ ? r.x.y : 0.f);
+        y.z = fmaxf(fmaf(v.z, s1.z, t1.z), 0.f) * k.z + at.z * fmaf(v.z, s2.z, t2.z) + (addx_ ? r.x.z : 0.f);
+        y.w = fmaxf(fmaf(v.w, s1.w, t1.w), 0.f) * k.w + at.w * fmaf(v.w, s2.w, t2.w) + (addx_ ? r.x.w : 0.f);
+        *reinterpret_cast<float4*>(op_ + p * 1024) = y;
     }
     DEVINL void finish(float*) {}
     DEVINL void finish_group(float*, int, int, int) {}
@@ -392,6 +470,33 @@ __host__ __device__ constexpr int tc_smem_bytes(int extra_floats) {
 
 // NT = 256 or 512 threads: HBM bandwidth on this part scales with the number of warps that issue loads
 // (tools/probe/inflight_probe2.cu: 8 warps/SM ~4 TB/s, 16 ~5.9, 32 ~6.1), so the stream-heavy instances run 2 x 512.
+template <class EP, class = void>
+struct ep_affine {
+    static constexpr bool value = false;
+};
+template <class EP>
+struct ep_affine<EP, decltype((void)EP::kAffine)> {
+    static constexpr bool value = EP::kAffine;
+};
+
+template <class EP, class = void>
+struct ep_pre {
+    using type = typename EP::Pre;
+};
+template <class EP>
+struct ep_pre<EP, decltype((void)sizeof(typename EP::PreA))> {
+    using type = typename EP::PreA;  // leaner per-row state of the affine interface
+};
+
+template <class AL, class = void>
+struct loader_batched {
+    static constexpr bool value = false;
+};
+template <class AL>
+struct loader_batched<AL, decltype((void)AL::kBatched)> {
+    static constexpr bool value = AL::kBatched;
+};
+
 template <int BN, int KTOT, int NS, int MINB, int PF, int NT, class AL, class EP>
 __global__ void __launch_bounds__(NT, MINB) gemm_tc_kernel(AL al, const float* __restrict__ Wimg, EP ep, int M) {
     constexpr int NK = KTOT / TC_KC;
@@ -452,6 +557,54 @@ __global__ void __launch_bounds__(NT, MINB) gemm_tc_kernel(AL al, const float* _
     unsigned char* a_dst0 = a_stage + kq * TC_LBO_A + (tid >> 3) * 16;
     constexpr uint32_t IDESC = umma_idesc_tf32(TC_BM, BN);
 
+    auto issue_mma = [&](int kc, int s) {  // thread 0, after the CTA barrier that follows the chunk's stores
+        mbar_wait(full_w + s, (kc / NS) & 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(a_stage + (size_t)s * TC_A_STAGE);
+        const uint32_t w_base = smem_u32(w_stage + (size_t)s * WBYTES);
+#pragma unroll
+        for (int q = 0; q < TC_KC / 8; ++q) {
+            const uint64_t da = umma_desc(a_base + 2 * q * TC_LBO_A, TC_LBO_A, 128);
+            const uint64_t db = umma_desc(w_base + 2 * q * (BN * 16), BN * 16, 128);
+            umma_tf32(tmem, da, db, IDESC, (kc > 0 || q > 0) ? 1u : 0u);
+        }
+        umma_commit(mma_done + s);
+    };
+
+    if constexpr (loader_batched<AL>::value) {
+        // loaders with several operand loads per element (TF-AR combine: 4): the raw loads of a whole chunk are issued
+        // as ONE batch and transformed afterwards -- otherwise the compiler serialises load -> transform per row and the
+        // A phase costs RPT * NK memory round trips instead of NK (measured: 31 % of the residual conv's warp time)
+        typename AL::Raw raw[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) raw[i] = al.raw_load(i, kq * 4);
+#pragma unroll
+        for (int kc = 0; kc < NK; ++kc) {
+            const int s = kc % NS;
+            if (kc >= NS) mbar_wait(mma_done + s, ((kc / NS) - 1) & 1);
+            if (NK > NS && tid == 0 && kc + PD < NK) {
+                const int c = kc + PD;
+                if (c >= NS) mbar_wait(mma_done + (c % NS), ((c / NS) - 1) & 1);
+                issue_w(c);
+            }
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                float4 v = al.xform_raw(raw[i], i, kc * TC_KC + kq * 4);
+                v.x = tf32r(v.x);
+                v.y = tf32r(v.y);
+                v.z = tf32r(v.z);
+                v.w = tf32r(v.w);
+                *reinterpret_cast<float4*>(a_dst0 + (size_t)s * TC_A_STAGE + i * (RS * 16)) = v;
+            }
+            fence_proxy_async();
+            if (kc + 1 < NK) {
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) raw[i] = al.raw_load(i, (kc + 1) * TC_KC + kq * 4);
+            }
+            __syncthreads();
+            if (tid == 0) issue_mma(kc, s);
+        }
+    } else {
     float4 areg[PF][RPT];
 #pragma unroll
     for (int c = 0; c < PF && c < NK; ++c) {
@@ -484,19 +637,8 @@ __global__ void __launch_bounds__(NT, MINB) gemm_tc_kernel(AL al, const float* _
             for (int i = 0; i < RPT; ++i) areg[kc % PF][i] = al.load(i, (kc + PF) * TC_KC + kq * 4);
         }
         __syncthreads();
-        if (tid == 0) {
-            mbar_wait(full_w + s, (kc / NS) & 1);
-            tc_fence_after();
-            const uint32_t a_base = smem_u32(a_stage + (size_t)s * TC_A_STAGE);
-            const uint32_t w_base = smem_u32(w_stage + (size_t)s * WBYTES);
-#pragma unroll
-            for (int q = 0; q < TC_KC / 8; ++q) {
-                const uint64_t da = umma_desc(a_base + 2 * q * TC_LBO_A, TC_LBO_A, 128);
-                const uint64_t db = umma_desc(w_base + 2 * q * (BN * 16), BN * 16, 128);
-                umma_tf32(tmem, da, db, IDESC, (kc > 0 || q > 0) ? 1u : 0u);
-            }
-            umma_commit(mma_done + s);
-        }
+        if (tid == 0) issue_mma(kc, s);
+    }
     }
     // accumulator complete once the last chunk's commit has arrived (commits complete in order)
     mbar_wait(mma_done + ((NK - 1) % NS), ((NK - 1) / NS) & 1);
@@ -513,12 +655,19 @@ __global__ void __launch_bounds__(NT, MINB) gemm_tc_kernel(AL al, const float* _
             const int col0 = hlf * (BN / NCG) + cb * 32;
             // all global loads of this 32x32 block are issued first and stay in flight while the
             // accumulator block is read from TMEM and transposed through shared memory
-            ep.prep(col0 + c4);
-            typename EP::Pre pre[8];
+            constexpr bool AFF = ep_affine<EP>::value;
+            const int rowq0 = row0 + q * 32;
+            if constexpr (AFF) ep.prep_block(rowq0, rsub, col0 + c4, M);
+            else ep.prep(col0 + c4);
+            typename ep_pre<EP>::type pre[8];
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
-                const int row = row0 + q * 32 + p * 4 + rsub;
-                pre[p] = ep.load(row < M ? row : M - 1, col0 + c4);
+                const int row = rowq0 + rsub + p * 4;
+                if constexpr (AFF) {
+                    if (row < M) pre[p] = ep.load_p(p);
+                } else {
+                    pre[p] = ep.load(row < M ? row : M - 1, col0 + c4);
+                }
             }
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
@@ -535,8 +684,11 @@ __global__ void __launch_bounds__(NT, MINB) gemm_tc_kernel(AL al, const float* _
             for (int p = 0; p < 8; ++p) {
                 const int r = p * 4 + rsub;
                 const float4 x = *reinterpret_cast<const float4*>(stg + r * TC_STG_LD + c4);
-                const int row = row0 + q * 32 + r;
-                if (row < M) ep.store4(row, col0 + c4, x, pre[p]);
+                const int row = rowq0 + r;
+                if (row < M) {
+                    if constexpr (AFF) ep.store_p(p, row, x, pre[p]);
+                    else ep.store4(row, col0 + c4, x, pre[p]);
+                }
             }
             __syncwarp();
         }
