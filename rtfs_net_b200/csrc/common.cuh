@@ -16,6 +16,10 @@ DEVINL uint32_t f2tf32(float x) {
     return r;
 }
 DEVINL float tf32r(float x) { return __uint_as_float(f2tf32(x)); }
+// cvt.rna.tf32.f32 is emulated on sm_100a (FSETP finite test + IADD + LOP3); without the NaN-payload guard it is two
+// integer instructions with the same result for every finite input and +-inf (round half away: add half an ulp of the
+// 10-bit mantissa to the magnitude bits, truncate)
+DEVINL float tf32r_fast(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
 // D(16x8) += A(16x8,row) * B(8x8,col);  lane = 4*g + t
 //   a0=(g,t) a1=(g+8,t) a2=(g,t+4) a3=(g+8,t+4);  b0=(k=t,n=g) b1=(k=t+4,n=g)

@@ -116,6 +116,9 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
                 // accumulator block is read from TMEM and transposed through shared memory
                 ep.prep(col0 + c4);
                 typename EP::Pre pre[8];
+#ifdef RTFS_PROBE_NO_STAGE
+                float pre_dummy = 0.f;
+#endif
 #pragma unroll
                 for (int p = 0; p < 8; ++p) {
                     const int row = row0 + q * 32 + p * 4 + rsub;
@@ -126,16 +129,24 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
                     uint32_t v[16];
                     tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + col0) + 16 * hh, v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#ifdef RTFS_PROBE_NO_STAGE
+                    pre_dummy += __uint_as_float(v[0]) + __uint_as_float(v[7]) + __uint_as_float(v[15]);
+#else
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         *reinterpret_cast<float4*>(stg + lane * TC_STG_LD + 16 * hh + 4 * i) =
                             make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+#endif
                 }
                 __syncwarp();
 #pragma unroll
                 for (int p = 0; p < 8; ++p) {
                     const int r = p * 4 + rsub;
+#ifdef RTFS_PROBE_NO_STAGE  // tools/probe/tcp_ablate.cu: timing without the staging reads (results meaningless)
+                    const float4 x = make_float4(pre_dummy, pre_dummy, pre_dummy, pre_dummy);
+#else
                     const float4 x = *reinterpret_cast<const float4*>(stg + r * TC_STG_LD + c4);
+#endif
                     const int row = row0 + q * 32 + r;
                     if (row < M) ep.store4(row, col0 + c4, x, pre[p]);
                 }
@@ -201,49 +212,72 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
             }
             cp_async_wait<0>();
         } else if constexpr (ASYNC == 2) {
+            // The producers are ISSUE-bound, not latency-bound (tools/probe/tcp_ablate.cu: ~125 instructions per warp and
+            // chunk, 16 warps -> the chunk period was ~1500 cycles whatever the memory did), so the loop is written
+            // tile by tile with the K chunk as a compile-time index: ring slot arithmetic, table offsets and global
+            // addresses become immediates off two per-tile row pointers, and the row-validity test is hoisted per tile.
+            static_assert(NK % PF == 0, "flat register stream: PF must divide the number of K chunks");
             const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-            const int G = my_tiles * NK;
             float4 raw[PF][RPT];
-            auto fetch = [&](int g, float4 (&dst)[RPT]) {
-                const int it = g / NK, kc = g - it * NK;
+            const float* pc[RPT];  // this thread's rows of the current tile (K offset kq*4), and of the next one
+            const float* pn[RPT];
+            bool vc[RPT], vn[RPT];
+            auto rows_of = [&](int it, const float* (&p)[RPT], bool (&v)[RPT]) {
                 const long long rbase = (long long)(blockIdx.x + it * gridDim.x) * TC_BM + (ptid >> 3);
 #pragma unroll
                 for (int i = 0; i < RPT; ++i) {
                     const long long row = rbase + RS * i;
-                    dst[i] = row < M ? ldg4(al.raw(row, kc * TC_KC + kq * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[i] = it < my_tiles && row < M;
+                    p[i] = al.raw(v[i] ? row : 0, kq * 4);
                 }
             };
+            rows_of(0, pc, vc);
 #pragma unroll
-            for (int c = 0; c < PF; ++c)
-                if (c < G) fetch(c, raw[c]);
-            for (int g0 = 0; g0 < G; g0 += PF) {
+            for (int c = 0; c < PF; ++c) {
 #pragma unroll
-                for (int j = 0; j < PF; ++j) {
-                    const int g = g0 + j;
-                    if (g >= G) break;
-                    const int it = g / NK, kc = g - it * NK;
-                    const int row0 = (blockIdx.x + it * gridDim.x) * TC_BM;
-                    if (kc == 0 && (!loader_tile_invariant<AL>::value || it == 0)) {
-                        al.init_p(row0, M, extra + (loader_tile_invariant<AL>::value ? 0 : (it & 1)) * AL::kExtra, ptid, TCP_PROD);
-                        if (AL::kExtra > 0) named_bar_sync(2, TCP_PROD);
-                    }
-                    const int s = g % NSA;
-                    if (g >= NSA) mbar_wait(empty_a + s, ((g / NSA) - 1) & 1);
+                for (int i = 0; i < RPT; ++i) raw[c][i] = vc[i] ? ldg4(pc[i] + c * TC_KC) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            int s = 0;          // ring slot of the next chunk, and the parity its empty barrier is waited with
+            uint32_t eph = 1;   // (first pass over the ring: nothing to wait for)
+            bool first_pass = true;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int row0 = (blockIdx.x + it * gridDim.x) * TC_BM;
+                rows_of(it + 1, pn, vn);
+                if (!loader_tile_invariant<AL>::value || it == 0) {
+                    al.init_p(row0, M, extra + (loader_tile_invariant<AL>::value ? 0 : (it & 1)) * AL::kExtra, ptid, TCP_PROD);
+                    if (AL::kExtra > 0) named_bar_sync(2, TCP_PROD);
+                }
+#pragma unroll
+                for (int kc = 0; kc < NK; ++kc) {
+                    if (!first_pass) mbar_wait(empty_a + s, eph);
 #pragma unroll
                     for (int i = 0; i < RPT; ++i) {
-                        const int row = row0 + (ptid >> 3) + RS * i;
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row < M) v = al.xform(raw[j][i], row, kc * TC_KC + kq * 4);
-                        v.x = tf32r(v.x);
-                        v.y = tf32r(v.y);
-                        v.z = tf32r(v.z);
-                        v.w = tf32r(v.w);
+                        if (vc[i]) v = al.xform(raw[kc % PF][i], row0 + (ptid >> 3) + RS * i, kc * TC_KC + kq * 4);
+                        v.x = tf32r_fast(v.x);
+                        v.y = tf32r_fast(v.y);
+                        v.z = tf32r_fast(v.z);
+                        v.w = tf32r_fast(v.w);
                         *reinterpret_cast<float4*>(a_dst0 + (size_t)s * TC_A_STAGE + i * (RS * 16)) = v;
                     }
                     fence_proxy_async();  // before the next loads are issued
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cta(full_a + s);
-                    if (g + PF < G) fetch(g + PF, raw[j]);
+                    if (++s == NSA) {
+                        s = 0;
+                        eph = first_pass ? 0u : eph ^ 1u;
+                        first_pass = false;
+                    }
+#pragma unroll
+                    for (int i = 0; i < RPT; ++i) {
+                        if (kc + PF < NK) raw[kc % PF][i] = vc[i] ? ldg4(pc[i] + (kc + PF) * TC_KC) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        else raw[kc % PF][i] = vn[i] ? ldg4(pn[i] + (kc + PF - NK) * TC_KC) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) {
+                    pc[i] = pn[i];
+                    vc[i] = vn[i];
                 }
             }
         } else {
@@ -285,16 +319,22 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
         // ================================================================= MMA issuer
         if (lane == 0) {
             int it = 0, ga = 0;
+#ifdef RTFS_PROBE_TIMING  // tools/probe/tcp_ablate.cu: cycles the MMA thread waits on each barrier kind
+            long long t_te = 0, t_fw = 0, t_fa = 0, t0 = clock64(), tq;
+#define PROBE_T(acc_, stmt) tq = clock64(); stmt; acc_ += clock64() - tq
+#else
+#define PROBE_T(acc_, stmt) stmt
+#endif
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
-                if (it >= 2) mbar_wait(tmem_empty + acc, ((it >> 1) - 1) & 1);
+                if (it >= 2) { PROBE_T(t_te, mbar_wait(tmem_empty + acc, ((it >> 1) - 1) & 1)); }
                 tc_fence_after();
 #pragma unroll 1
                 for (int kc = 0; kc < NK; ++kc, ++ga) {
                     const int s = ga % NSA;
                     const int ws = WRES ? kc : ga % NSW;
-                    mbar_wait(full_w + ws, WRES ? 0 : (ga / NSW) & 1);
-                    mbar_wait(full_a + s, (ga / NSA) & 1);
+                    PROBE_T(t_fw, mbar_wait(full_w + ws, WRES ? 0 : (ga / NSW) & 1));
+                    PROBE_T(t_fa, mbar_wait(full_a + s, (ga / NSA) & 1));
                     tc_fence_after();
                     const uint32_t a_base = smem_u32(a_stage + (size_t)s * TC_A_STAGE);
                     const uint32_t w_base = smem_u32(w_stage + (size_t)ws * WBYTES);
@@ -309,6 +349,9 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
                 }
                 umma_commit(tmem_full + acc);
             }
+#ifdef RTFS_PROBE_TIMING
+            if (blockIdx.x < 1) printf("cta %d mma thread: total %lld cycles, wait tmem_empty %lld, full_w %lld, full_a %lld (tiles %d)\n", blockIdx.x, clock64() - t0, t_te, t_fw, t_fa, it);
+#endif
         }
     } else {
         // ================================================================= weight loader
@@ -324,6 +367,12 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
                     for (int kc = 0; kc < NK; ++kc, ++gw) {
                         const int ws = gw % NSW, use = gw / NSW;
                         if (use > 0) mbar_wait(empty_w + ws, (use - 1) & 1);
+#ifdef RTFS_PROBE_W_ONCE  // tools/probe/tcp_ablate.cu: timing without the weight stream (stale slabs, results meaningless)
+                        if (gw >= NSW) {
+                            mbar_arrive_cta(full_w + ws);
+                            continue;
+                        }
+#endif
                         mbar_expect_tx(full_w + ws, WBYTES);
                         bulk_g2s(w_stage + (size_t)ws * WBYTES, Wimg + (size_t)kc * (BN * TC_KC), WBYTES, full_w + ws);
                     }
