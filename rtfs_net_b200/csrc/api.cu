@@ -608,7 +608,7 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out, boo
         }
         {
             // f1 = TFAR_fus1(d1, g) formed on the fly -> the two global convs of concat_layers.0
-            XrTfar xf{le1, gg1, ge1, d.Tc, d.Fc, d.Tc, d.Fc,
+            XrTfarP xf{le1, gg1, ge1, d.Tc, d.Fc, d.Tc, d.Fc,
                       c.gln(RTFS_ST_F1L, RTFS_P_F1_LG, RTFS_P_F1_LB, ncomp), c.gln(RTFS_ST_F1G, RTFS_P_F1_GG, RTFS_P_F1_GB, ncomp),
                       c.gln(RTFS_ST_F1E, RTFS_P_F1_EG, RTFS_P_F1_EB, ncomp)};
             DrArgs<2> a{};
@@ -616,18 +616,26 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out, boo
             a.w[0] = P[RTFS_P_C0_EW]; a.out[0] = gec; a.sums[0] = c.stat(RTFS_ST_C0E);
             a.w[1] = P[RTFS_P_C0_GW]; a.out[1] = ggc; a.sums[1] = c.stat(RTFS_ST_C0G);
             STAGE(RTFS_SG_TFAR_CAT_GLOBAL);
-            CK((launch_dwroll<XrTfar, 2, false, 128, true, 4>(xf, a, d.B, c.st)));
+            CK((launch_dwroll<XrTfarP, 2, false, 128, 4>(xf, a, d.B, c.st)));
         }
         {
             // f0 = TFAR_fus0(d0, g) formed on the fly -> local conv of concat_layers.0
-            XrTfar xf{le0, gg0, ge0, d.T, d.F, d.Tc, d.Fc,
-                      c.gln(RTFS_ST_F0L, RTFS_P_F0_LG, RTFS_P_F0_LB, nfull), c.gln(RTFS_ST_F0G, RTFS_P_F0_GG, RTFS_P_F0_GB, ncomp),
-                      c.gln(RTFS_ST_F0E, RTFS_P_F0_EG, RTFS_P_F0_EB, ncomp)};
             DrArgs<1> a{};
             a.Ti = d.T; a.Fi = d.F;
             a.w[0] = P[RTFS_P_C0_LW]; a.out[0] = lec; a.sums[0] = c.stat(RTFS_ST_C0L);
             STAGE(RTFS_SG_TFAR_CAT_LOCAL);
-            CK((launch_dwroll<XrTfar, 1, false, 288, false>(xf, a, d.B, c.st)));
+            static const bool scalar = env_flag("RTFS_SCALAR_TFAR");  // first-generation kernel (sigmoid per window column)
+            if (scalar) {
+                XrTfar xf{le0, gg0, ge0, d.T, d.F, d.Tc, d.Fc,
+                          c.gln(RTFS_ST_F0L, RTFS_P_F0_LG, RTFS_P_F0_LB, nfull), c.gln(RTFS_ST_F0G, RTFS_P_F0_GG, RTFS_P_F0_GB, ncomp),
+                          c.gln(RTFS_ST_F0E, RTFS_P_F0_EG, RTFS_P_F0_EB, ncomp)};
+                CK((launch_dwroll_scalar<XrTfar, 1, false, 288>(xf, a, d.B, c.st)));
+            } else {
+                XrTfarP xf{le0, gg0, ge0, d.T, d.F, d.Tc, d.Fc,
+                           c.gln(RTFS_ST_F0L, RTFS_P_F0_LG, RTFS_P_F0_LB, nfull), c.gln(RTFS_ST_F0G, RTFS_P_F0_GG, RTFS_P_F0_GB, ncomp),
+                           c.gln(RTFS_ST_F0E, RTFS_P_F0_EG, RTFS_P_F0_EB, ncomp)};
+                CK((launch_dwroll<XrTfarP, 1, false, 288>(xf, a, d.B, c.st)));
+            }
         }
     } else {
         // S10-S12 TF-AR units                                                  tdanet.py:124-129, layers/fusion.py:54-69
