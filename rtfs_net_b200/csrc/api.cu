@@ -213,7 +213,9 @@ int run_encoder(const Ctx& c, const float* wav, float* a0, int L) {
     StftArgs sa{wav, c.P[RTFS_P_WINDOW], c.P[RTFS_P_COSTAB], c.P[RTFS_P_SINTAB], c.buf(RTFS_WS_SPEC), L, d.T};
     {
         STAGE(RTFS_SG_STFT);
-        stft_kernel<<<dim3(d.T, d.B), 288, 0, c.st>>>(sa);
+        static const bool legacy_fe = env_flag("RTFS_LEGACY_FRONTEND");  // one frame per CTA (first generation)
+        if (legacy_fe) stft_kernel<<<dim3(d.T, d.B), 288, 0, c.st>>>(sa);
+        else stft16_kernel<<<dim3((d.T + FE_FR - 1) / FE_FR, d.B), 160, 0, c.st>>>(sa);
         CK(cudaGetLastError());
     }
     CKN(cudaMemsetAsync(c.stat(RTFS_ST_A0), 0, sizeof(double) * 2 * d.B, c.st));
@@ -774,7 +776,9 @@ int run_decoder(const Ctx& c, const float* z, float* wav_out, int L) {
     }
     IstftArgs ia{c.buf(RTFS_WS_Q18), c.P[RTFS_P_WINDOW], c.P[RTFS_P_COSTAB], c.P[RTFS_P_SINTAB], wav_out, L, d.T};
     STAGE(RTFS_SG_DEC_ISTFT);
-    dec_istft_kernel<<<dim3((L + 127) / 128, d.B), 256, 0, c.st>>>(ia);
+    static const bool legacy_fe = env_flag("RTFS_LEGACY_FRONTEND");
+    if (legacy_fe) dec_istft_kernel<<<dim3((L + 127) / 128, d.B), 256, 0, c.st>>>(ia);
+    else dec_istft16_kernel<<<dim3(((L + 127) / 128 + FE_FR - 1) / FE_FR, d.B), 256, 0, c.st>>>(ia);
     CK(cudaGetLastError());
     return 0;
 }
