@@ -16,6 +16,12 @@ namespace rtfs {
 
 constexpr int AC_LBO = 128 * 16 + 16;    // activation slab: 16 K-pieces x (128 rows x 16 B + pad)
 constexpr int AC_A_BYTES = 16 * AC_LBO;  // 33024
+// CTAs per SM: the per-CTA chain (load -> MMA -> three TMEM passes) is latency-bound, so as many as registers (MODE 0:
+// 168) and shared memory (MODE 1: the transpose staging aliases the activation slab) allow
+template <int MODE>
+__host__ __device__ constexpr int ac_ctas() { return MODE == 0 ? 3 : 4; }
+template <int MODE>
+__host__ __device__ constexpr int ac_a_area() { return MODE == 1 ? 4 * 32 * 68 * 4 : AC_A_BYTES; }  // 34816 / 33024
 
 struct AttConvArgs {
     const float* x;      // (B*Tc, 64 f, 64 c)
@@ -34,7 +40,7 @@ struct AttConvArgs {
 
 template <int N, int MODE>
 constexpr int att_conv_smem() {
-    return AC_A_BYTES + N * 64 * 4 + 2 * 4 * 16 * 4 + 64 + (MODE == 1 ? 4 * 32 * 68 * 4 : 0);
+    return ac_a_area<MODE>() + N * 64 * 4 + 2 * 4 * 16 * 4 + 64;
 }
 
 // group g of MODE 0: columns [c0, c0 + E)
@@ -52,14 +58,14 @@ DEVINL void ac_group(int g, int& c0, int& E) {
 }
 
 template <int N, int MODE>
-__global__ void __launch_bounds__(128, 2) att_conv_ln_tc_kernel(AttConvArgs a) {
+__global__ void __launch_bounds__(128, ac_ctas<MODE>()) att_conv_ln_tc_kernel(AttConvArgs a) {
     constexpr int NG = MODE == 0 ? 12 : 1;
     constexpr int TCOLS = N <= 64 ? 64 : 128;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* a_slab = smem_raw;
-    unsigned char* w_slab = smem_raw + AC_A_BYTES;
+    unsigned char* w_slab = smem_raw + ac_a_area<MODE>();
     float* part = reinterpret_cast<float*>(w_slab + N * 64 * 4);  // [pass 2][warp 4][16]
-    float* stg_all = reinterpret_cast<float*>(smem_raw + AC_A_BYTES + N * 64 * 4 + 2 * 4 * 16 * 4 + 64);  // MODE 1: 4 x [32][68]
+    float* stg_all = reinterpret_cast<float*>(smem_raw);  // MODE 1: 4 x [32][68], aliases the slab (free once the MMAs have completed)
     uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * 4 * 16);
     uint64_t* w_ready = bars;
     uint64_t* mma_done = bars + 1;
@@ -277,7 +283,7 @@ inline cudaError_t launch_att_conv_tc(const AttConvArgs& a, cudaStream_t st) {
         configured = true;
     }
     const int npairs = (a.nframes + 1) / 2;
-    const int grid = npairs < 296 ? npairs : 296;
+    const int grid = npairs < 148 * ac_ctas<MODE>() ? npairs : 148 * ac_ctas<MODE>();
     kern<<<grid, 128, smem, st>>>(a);
     return cudaGetLastError();
 }

@@ -162,7 +162,10 @@ struct AttnArgs {
 constexpr int AT_QT = 32, AT_KR = 32, AT_LDQ = 260, AT_LDV = 136;
 // Q tile + score tile + one K/V chunk of AT_KR keys: 83 KB at 125 frames -> two CTAs per SM overlap each other's
 // load -> wait -> MMA rounds
-inline int attn_smem_floats(int tk_pad) { return AT_QT * AT_LDQ + AT_QT * (tk_pad + 4) + AT_KR * AT_LDQ; }
+inline int attn_smem_floats(int tk_pad) {  // Q tile + score tile + max(one K chunk, two V chunks)
+    const int kv = AT_KR * AT_LDQ > 2 * AT_KR * AT_LDV ? AT_KR * AT_LDQ : 2 * AT_KR * AT_LDV;
+    return AT_QT * AT_LDQ + AT_QT * (tk_pad + 4) + kv;
+}
 
 __global__ void __launch_bounds__(256, 2) attn_core_kernel(AttnArgs a) {
     extern __shared__ __align__(16) float sm[];
@@ -218,6 +221,23 @@ __global__ void __launch_bounds__(256, 2) attn_core_kernel(AttnArgs a) {
         }
         __syncthreads();
     }
+    // ---- O = P V, 128 value columns at a time: warp (wm, wn) -> 16 queries x 32 columns.  The 8 x nkc V chunks
+    //      (32 keys x 128 columns) form one stream through TWO buffers: chunk s+1 is in flight (cp.async) while the
+    //      MMAs of chunk s run, and chunk 0 is fetched behind the softmax (every round used to expose an L2 round trip).
+    const int b = bh / a.H, h = bh - b * a.H;
+    const int nst = 8 * nkc;
+    auto issue_v = [&](int s_) {
+        const int nc_ = s_ / nkc, kc_ = s_ - nc_ * nkc;
+        float* dstb = KV + (s_ & 1) * (AT_KR * AT_LDV);
+        for (int i = tid; i < AT_KR * 32; i += 256) {
+            const int r = i >> 5, c4 = i & 31;
+            const int key = kc_ * AT_KR + r;
+            const bool valid = key < Tc;
+            cp_async16(dstb + r * AT_LDV + c4 * 4, Vg + (long long)(valid ? key : 0) * 1024 + nc_ * 128 + c4 * 4, valid);
+        }
+        cp_async_commit();
+    };
+    issue_v(0);
     // ---- softmax over keys (rows of Ss); padded keys get probability 0
     for (int r = warp * 4; r < warp * 4 + 4; ++r) {
         float* row = Ss + r * SLD;
@@ -234,23 +254,20 @@ __global__ void __launch_bounds__(256, 2) attn_core_kernel(AttnArgs a) {
         const float inv = 1.f / s;
         for (int j = lane; j < a.tk_pad; j += 32) row[j] = j < Tc ? tf32r(row[j] * inv) : 0.f;
     }
-    __syncthreads();
-    // ---- O = P V, 128 value columns at a time: warp (wm, wn) -> 16 queries x 32 columns
-    const int b = bh / a.H, h = bh - b * a.H;
+    float acc[4][4];
+    int st = 0;
     for (int nc = 0; nc < 8; ++nc) {
-        float acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-        for (int kc = 0; kc < nkc; ++kc) {
-            for (int i = tid; i < AT_KR * 32; i += 256) {
-                const int r = i >> 5, c4 = i & 31;
-                const int key = kc * AT_KR + r;
-                const bool valid = key < Tc;
-                cp_async16(KV + r * AT_LDV + c4 * 4, Vg + (long long)(valid ? key : 0) * 1024 + nc * 128 + c4 * 4, valid);
+        for (int kc = 0; kc < nkc; ++kc, ++st) {
+            if (st + 1 < nst) {
+                issue_v(st + 1);      // into the buffer chunk st-1 was read from (all warps passed the barrier below)
+                cp_async_wait<1>();   // chunk st has landed (this thread's pieces)
+            } else {
+                cp_async_wait<0>();
             }
-            cp_async_commit();
-            cp_async_wait<0>();
-            __syncthreads();
+            __syncthreads();          // everyone's pieces of chunk st (and, the first time, the softmax rows)
+            const float* Vb = KV + (st & 1) * (AT_KR * AT_LDV);
 #pragma unroll
             for (int ks = 0; ks < AT_KR / 8; ++ks) {
                 uint32_t af[4];
@@ -261,12 +278,12 @@ __global__ void __launch_bounds__(256, 2) attn_core_kernel(AttnArgs a) {
                 af[3] = __float_as_uint(p[8 * SLD + 4]);
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) {
-                    const float* q = KV + (ks * 8 + t) * AT_LDV + wn * 32 + ni * 8 + g;
+                    const float* q = Vb + (ks * 8 + t) * AT_LDV + wn * 32 + ni * 8 + g;
                     uint32_t bf[2] = {__float_as_uint(q[0]), __float_as_uint(q[4 * AT_LDV])};
                     mma_tf32(acc[ni], af, bf);
                 }
             }
-            __syncthreads();
+            __syncthreads();          // chunk st's buffer may be refilled by the next iteration's issue
         }
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
