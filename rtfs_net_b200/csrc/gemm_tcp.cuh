@@ -14,6 +14,7 @@
 //                          otherwise 32-wide K slabs stream through an NSW-stage ring (cp.async.bulk + mbarrier)
 #pragma once
 #include <cstdio>
+#include <type_traits>
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
@@ -28,6 +29,12 @@ struct loader_tile_invariant<AL, decltype((void)AL::kTileInvariant)> {
     static constexpr bool value = AL::kTileInvariant;
 };
 
+#ifndef TCP_AFFINE
+#define TCP_AFFINE 0   // block-pointer epilogue addressing (gemm_tc.cuh): its 64 live load registers spill under the same cap
+#endif
+#ifndef TCP_BATCHED
+#define TCP_BATCHED 0  // batched raw loads in the per-tile producer: 64 live registers, spills under the 96-register cap of 18 warps
+#endif
 constexpr int TCP_EPI = 256;  // epilogue threads (warps 0-7); then NPROD producer threads, the MMA warp and the weight warp
 
 DEVINL void mbar_arrive_cta(uint64_t* bar) {
@@ -114,15 +121,22 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
                 const int col0 = hlf * (BN / 2) + cb * 32;
                 // all global loads of this 32x32 block are issued first and stay in flight while the
                 // accumulator block is read from TMEM and transposed through shared memory
-                ep.prep(col0 + c4);
-                typename EP::Pre pre[8];
+                constexpr bool AFF = ep_affine<EP>::value && TCP_AFFINE;
+                const int rowq0 = row0 + q * 32;
+                if constexpr (AFF) ep.prep_block(rowq0, rsub, col0 + c4, M);
+                else ep.prep(col0 + c4);
+                typename std::conditional<AFF, typename ep_pre<EP>::type, typename EP::Pre>::type pre[8];
 #ifdef RTFS_PROBE_NO_STAGE
                 float pre_dummy = 0.f;
 #endif
 #pragma unroll
                 for (int p = 0; p < 8; ++p) {
-                    const int row = row0 + q * 32 + p * 4 + rsub;
-                    pre[p] = ep.load(row < M ? row : M - 1, col0 + c4);
+                    const int row = rowq0 + rsub + p * 4;
+                    if constexpr (AFF) {
+                        if (row < M) pre[p] = ep.load_p(p);
+                    } else {
+                        pre[p] = ep.load(row < M ? row : M - 1, col0 + c4);
+                    }
                 }
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
@@ -147,8 +161,11 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
 #else
                     const float4 x = *reinterpret_cast<const float4*>(stg + r * TC_STG_LD + c4);
 #endif
-                    const int row = row0 + q * 32 + r;
-                    if (row < M) ep.store4(row, col0 + c4, x, pre[p]);
+                    const int row = rowq0 + r;
+                    if (row < M) {
+                        if constexpr (AFF) ep.store_p(p, row, x, pre[p]);
+                        else ep.store4(row, col0 + c4, x, pre[p]);
+                    }
                 }
                 __syncwarp();
             }
@@ -286,6 +303,35 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
             const int row0 = tile * TC_BM;
             al.init_p(row0, M, extra + (it & 1) * AL::kExtra, ptid, TCP_PROD);
             if (AL::kExtra > 0) named_bar_sync(2, TCP_PROD);  // the tile's loader table is complete
+            if constexpr (loader_batched<AL>::value && TCP_BATCHED) {
+                // several operand loads per element (TF-AR combine): one chunk's raw loads are issued as a batch and
+                // transformed afterwards (see gemm_tc_kernel), the next chunk's batch flies behind the stores
+                typename AL::Raw raw[RPT];
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) raw[i] = al.raw_load(i, kq * 4);
+#pragma unroll
+                for (int kc = 0; kc < NK; ++kc, ++ga) {
+                    const int s = ga % NSA, use = ga / NSA;
+                    if (use > 0) mbar_wait(empty_a + s, (use - 1) & 1);
+#pragma unroll
+                    for (int i = 0; i < RPT; ++i) {
+                        float4 v = al.xform_raw(raw[i], i, kc * TC_KC + kq * 4);
+                        v.x = tf32r_fast(v.x);
+                        v.y = tf32r_fast(v.y);
+                        v.z = tf32r_fast(v.z);
+                        v.w = tf32r_fast(v.w);
+                        *reinterpret_cast<float4*>(a_dst0 + (size_t)s * TC_A_STAGE + i * (RS * 16)) = v;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cta(full_a + s);
+                    if (kc + 1 < NK) {
+#pragma unroll
+                        for (int i = 0; i < RPT; ++i) raw[i] = al.raw_load(i, (kc + 1) * TC_KC + kq * 4);
+                    }
+                }
+                continue;
+            }
             float4 areg[PF][RPT];
 #pragma unroll
             for (int c = 0; c < PF; ++c) {
