@@ -29,6 +29,9 @@ struct loader_tile_invariant<AL, decltype((void)AL::kTileInvariant)> {
     static constexpr bool value = AL::kTileInvariant;
 };
 
+#ifndef TCP_REGSPLIT
+#define TCP_REGSPLIT 0   // setmaxnreg split (works; measured 0.74 vs 0.71 ms for the residual conv: the 72-register producers lose more than the epilogue gains)
+#endif
 #ifndef TCP_AFFINE
 #define TCP_AFFINE 0   // block-pointer epilogue addressing (gemm_tc.cuh): its 64 live load registers spill under the same cap
 #endif
@@ -105,7 +108,12 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
     const uint32_t tmem = *tmem_slot;
     constexpr uint32_t IDESC = umma_idesc_tf32(TC_BM, BN);
 
+    // Register split (8-warp producer configuration only): 18 warps cap every thread at 96 registers, which spills the
+    // residual epilogue's 64 in-flight load registers; the producer warpgroups hand 24 registers per thread to the
+    // epilogue warpgroups (setmaxnreg works on aligned groups of 4 warps; the MMA / weight warps keep their 96).
+    constexpr bool REGSPLIT = TCP_REGSPLIT && NPROD == 256;
     if (warp < 8) {
+        if constexpr (REGSPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
         // ================================================================= epilogue
         const int q = warp & 3, hlf = warp >> 2;
         float* stg = stg_all + warp * (32 * TC_STG_LD);
@@ -121,7 +129,7 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
                 const int col0 = hlf * (BN / 2) + cb * 32;
                 // all global loads of this 32x32 block are issued first and stay in flight while the
                 // accumulator block is read from TMEM and transposed through shared memory
-                constexpr bool AFF = ep_affine<EP>::value && TCP_AFFINE;
+                constexpr bool AFF = ep_affine<EP>::value && TCP_AFFINE && REGSPLIT;
                 const int rowq0 = row0 + q * 32;
                 if constexpr (AFF) ep.prep_block(rowq0, rsub, col0 + c4, M);
                 else ep.prep(col0 + c4);
@@ -175,6 +183,7 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
             ep.finish_group(scratch, tid, TCP_EPI, 1);
         }
     } else if (warp < MMA_WARP) {
+        if constexpr (REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
         // ================================================================= A producers
         const int ptid = tid - TCP_EPI;
         const int kq = ptid & 7;
