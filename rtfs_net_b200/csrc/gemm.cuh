@@ -317,17 +317,52 @@ struct Im2colLoader {
 struct Im2colLoader3x {
     Im2colLoader base;
     static constexpr int kExtra = 0;
-    DEVINL void init(int row0, int M, float* e) { base.init(row0, M, e); }
+    // per-tile state of the persistent producers: the (b, t, f) decomposition of a thread's 4 rows is done once per tile
+    // (one division, then increments) and its two taps are fixed by its K piece, so a load is two predicated 8-byte reads
+    const float* rp_[4];  // &spec[b][t][f][0] of row i
+    int t_[4], f_[4];
+    int oa_, ob_, dia_, dja_, dib_, djb_;  // element offsets and (dt, df) of taps 2*kq and 2*kq+1 (dia_ = 9: no such tap)
+    DEVINL void init(int row0, int M, float* e) { init_p(row0, M, e, threadIdx.x, blockDim.x); }
     DEVINL void init_p(int row0, int M, float*, int ptid, int nthr) {
         base.row0_ = row0 + (ptid >> 3);
         base.rs_ = nthr >> 3;
         base.M_ = M;
+        const int T = base.T, F = base.F, P = T * F;
+        const int ta = 2 * (ptid & 7), tb = ta + 1;
+        dia_ = ta < 9 ? ta / 3 - 1 : 9;
+        dja_ = ta < 9 ? ta % 3 - 1 : 0;
+        dib_ = tb < 9 ? tb / 3 - 1 : 9;
+        djb_ = tb < 9 ? tb % 3 - 1 : 0;
+        oa_ = (dia_ * F + dja_) * 2;
+        ob_ = (dib_ * F + djb_) * 2;
+        int row = base.row0_ < M ? base.row0_ : M - 1;
+        int b = row / P, p = row - b * P;
+        int t = p / F, f = p - t * F;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            rp_[i] = base.spec + (((long long)b * T + t) * F + f) * 2;
+            t_[i] = t;
+            f_[i] = f;
+            f += base.rs_;                 // next row of this thread: rs_ (= 32 or 64) positions further
+            while (f >= F) {
+                f -= F;
+                if (++t == T) {
+                    t = 0;
+                    ++b;
+                }
+            }
+        }
     }
     DEVINL float4 load(int i, int k) const {
-        const int seg = k >> 5;
-        const float4 v = base.load(i, k & 31);
+        if (base.row0_ + base.rs_ * i >= base.M_) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const int T = base.T, F = base.F;
+        const int ta = t_[i] + dia_, fa = f_[i] + dja_, tb = t_[i] + dib_, fb = f_[i] + djb_;
+        float2 u = make_float2(0.f, 0.f), w = make_float2(0.f, 0.f);
+        if (dia_ != 9 && ta >= 0 && ta < T && fa >= 0 && fa < F) u = ldg2(rp_[i] + oa_);
+        if (dib_ != 9 && tb >= 0 && tb < T && fb >= 0 && fb < F) w = ldg2(rp_[i] + ob_);
+        const float4 v = make_float4(u.x, u.y, w.x, w.y);
         const float4 hi = make_float4(tf32r(v.x), tf32r(v.y), tf32r(v.z), tf32r(v.w));
-        if (seg != 1) return hi;
+        if ((k >> 5) != 1) return hi;
         return make_float4(tf32r(v.x - hi.x), tf32r(v.y - hi.y), tf32r(v.z - hi.z), tf32r(v.w - hi.w));
     }
 };
