@@ -536,7 +536,7 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out, boo
             CK(launch_gateproj_wide(ga, c.st));
         } else if (use_tc()) {
             StatsEpi4 ep{p_pre, 64, P[RTFS_P_PJ_B], c.stat(RTFS_ST_PJ), (int)d.P, d.B};
-            if (use_persistent(1)) CK((launch_gemm_tcp<64, 256, 6, 1, true, 4, 2, 512>(al, P[RTFS_P_PJ_WI], ep, M, c.st)));
+            if (use_persistent(1)) CK((launch_gemm_tcp<64, 256, 4, 1, true, 4, 2, 512>(al, P[RTFS_P_PJ_WI], ep, M, c.st)));
                         else CK((launch_gemm_tc<64, 256, 4, 2, 2, 256>(al, P[RTFS_P_PJ_WI], ep, M, c.st)));
         } else {
             StatsEpi ep{p_pre, 64, P[RTFS_P_PJ_B], c.stat(RTFS_ST_PJ), (int)d.P, d.B};
