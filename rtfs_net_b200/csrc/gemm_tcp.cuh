@@ -276,16 +276,19 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
 #pragma unroll
                 for (int kc = 0; kc < NK; ++kc) {
                     if (!first_pass) mbar_wait(empty_a + s, eph);
+                    // rows past M are transformed like any other (zeros in): their accumulator rows are never stored, and
+                    // transforming all rows before the first store lets the per-channel table loads be shared between them
+                    float4 v[RPT];
 #pragma unroll
                     for (int i = 0; i < RPT; ++i) {
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (vc[i]) v = al.xform(raw[kc % PF][i], row0 + (ptid >> 3) + RS * i, kc * TC_KC + kq * 4);
-                        v.x = tf32r_fast(v.x);
-                        v.y = tf32r_fast(v.y);
-                        v.z = tf32r_fast(v.z);
-                        v.w = tf32r_fast(v.w);
-                        *reinterpret_cast<float4*>(a_dst0 + (size_t)s * TC_A_STAGE + i * (RS * 16)) = v;
+                        v[i] = al.xform(raw[kc % PF][i], row0 + (ptid >> 3) + RS * i, kc * TC_KC + kq * 4);
+                        v[i].x = tf32r_fast(v[i].x);
+                        v[i].y = tf32r_fast(v[i].y);
+                        v[i].z = tf32r_fast(v[i].z);
+                        v[i].w = tf32r_fast(v[i].w);
                     }
+#pragma unroll
+                    for (int i = 0; i < RPT; ++i) *reinterpret_cast<float4*>(a_dst0 + (size_t)s * TC_A_STAGE + i * (RS * 16)) = v[i];
                     fence_proxy_async();  // before the next loads are issued
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cta(full_a + s);
