@@ -388,6 +388,7 @@ struct MaskEpi4 {
     float* z;
     const float* bias;
     const float* a0;
+    static constexpr bool kRollPre = false;  // rolling prefetch of the next block (gemm_tcp.cuh ROLL): measured slower (0.96 vs 0.80 ms, loaded values spill at 72 registers)
     struct Pre {
         float2 er, ei;
     };
@@ -486,6 +487,15 @@ struct ep_pre {
 template <class EP>
 struct ep_pre<EP, decltype((void)sizeof(typename EP::PreA))> {
     using type = typename EP::PreA;  // leaner per-row state of the affine interface
+};
+
+template <class EP, class = void>
+struct ep_roll {
+    static constexpr bool value = false;
+};
+template <class EP>
+struct ep_roll<EP, decltype((void)EP::kRollPre)> {
+    static constexpr bool value = EP::kRollPre;
 };
 
 template <class AL, class = void>

@@ -119,6 +119,21 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
         float* stg = stg_all + warp * (32 * TC_STG_LD);
         const int rsub = lane >> 3, c4 = (lane & 7) * 4;
         int it = 0;
+        constexpr bool AFF = ep_affine<EP>::value && TCP_AFFINE && REGSPLIT;
+        // ROLL: the epilogue's global inputs of block n+1 (next 32 columns, or the first block of this CTA's next tile) are
+        // requested right after the matching rows of block n are stored -- same registers, but a warp no longer exposes one
+        // memory round trip per block (4 per tile for the mask epilogue, which made the epilogue warps the critical path)
+        constexpr bool ROLL = ep_roll<EP>::value && !AFF;
+        typename std::conditional<AFF, typename ep_pre<EP>::type, typename EP::Pre>::type pre[8];
+        if constexpr (ROLL) {
+            if ((int)blockIdx.x < ntiles) {
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    const int row = blockIdx.x * TC_BM + q * 32 + rsub + p * 4;
+                    pre[p] = ep.load(row < M ? row : M - 1, hlf * (BN / 2) + c4);
+                }
+            }
+        }
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int acc = it & 1, row0 = tile * TC_BM;
             ep.init(row0, M);
@@ -129,21 +144,21 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
                 const int col0 = hlf * (BN / 2) + cb * 32;
                 // all global loads of this 32x32 block are issued first and stay in flight while the
                 // accumulator block is read from TMEM and transposed through shared memory
-                constexpr bool AFF = ep_affine<EP>::value && TCP_AFFINE && REGSPLIT;
                 const int rowq0 = row0 + q * 32;
                 if constexpr (AFF) ep.prep_block(rowq0, rsub, col0 + c4, M);
                 else ep.prep(col0 + c4);
-                typename std::conditional<AFF, typename ep_pre<EP>::type, typename EP::Pre>::type pre[8];
 #ifdef RTFS_PROBE_NO_STAGE
                 float pre_dummy = 0.f;
 #endif
+                if constexpr (!ROLL) {
 #pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    const int row = rowq0 + rsub + p * 4;
-                    if constexpr (AFF) {
-                        if (row < M) pre[p] = ep.load_p(p);
-                    } else {
-                        pre[p] = ep.load(row < M ? row : M - 1, col0 + c4);
+                    for (int p = 0; p < 8; ++p) {
+                        const int row = rowq0 + rsub + p * 4;
+                        if constexpr (AFF) {
+                            if (row < M) pre[p] = ep.load_p(p);
+                        } else {
+                            pre[p] = ep.load(row < M ? row : M - 1, col0 + c4);
+                        }
                     }
                 }
 #pragma unroll
@@ -173,6 +188,14 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
                     if (row < M) {
                         if constexpr (AFF) ep.store_p(p, row, x, pre[p]);
                         else ep.store4(row, col0 + c4, x, pre[p]);
+                    }
+                    if constexpr (ROLL) {
+                        const bool lastb = cb + 1 == BN / 64;
+                        const int ntile = lastb ? tile + (int)gridDim.x : tile;
+                        if (ntile < ntiles) {
+                            const int nrow = ntile * TC_BM + q * 32 + r;
+                            pre[p] = ep.load(nrow < M ? nrow : M - 1, (lastb ? hlf * (BN / 2) : col0 + 32) + c4);
+                        }
                     }
                 }
                 __syncwarp();
