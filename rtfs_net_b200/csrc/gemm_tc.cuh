@@ -388,6 +388,7 @@ struct MaskEpi4 {
     float* z;
     const float* bias;
     const float* a0;
+    static constexpr int kTcpEpiRegs = 104;  // persistent kernel: register re-allocation towards the epilogue warps (setmaxnreg)
     static constexpr bool kRollPre = false;  // rolling prefetch of the next block (gemm_tcp.cuh ROLL): measured slower (0.96 vs 0.80 ms, loaded values spill at 72 registers)
     struct Pre {
         float2 er, ei;
@@ -487,6 +488,15 @@ struct ep_pre {
 template <class EP>
 struct ep_pre<EP, decltype((void)sizeof(typename EP::PreA))> {
     using type = typename EP::PreA;  // leaner per-row state of the affine interface
+};
+
+template <class EP, class = void>
+struct ep_epi_regs {
+    static constexpr int value = 0;
+};
+template <class EP>
+struct ep_epi_regs<EP, decltype((void)EP::kTcpEpiRegs)> {
+    static constexpr int value = EP::kTcpEpiRegs;
 };
 
 template <class EP, class = void>

@@ -112,8 +112,12 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
     // residual epilogue's 64 in-flight load registers; the producer warpgroups hand 24 registers per thread to the
     // epilogue warpgroups (setmaxnreg works on aligned groups of 4 warps; the MMA / weight warps keep their 96).
     constexpr bool REGSPLIT = TCP_REGSPLIT && NPROD == 256;
+    // 16-producer-warp configuration (26 warps, 72 registers each): epilogues that hold global inputs in registers (S^3 mask)
+    // ask for 104 through EP::kTcpEpiRegs, the producers drop to 56
+    constexpr bool REGSPLIT16 = NPROD == 512 && ep_epi_regs<EP>::value > 0;
     if (warp < 8) {
         if constexpr (REGSPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+        if constexpr (REGSPLIT16) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ================================================================= epilogue
         const int q = warp & 3, hlf = warp >> 2;
         float* stg = stg_all + warp * (32 * TC_STG_LD);
@@ -207,6 +211,7 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
         }
     } else if (warp < MMA_WARP) {
         if constexpr (REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        if constexpr (REGSPLIT16) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         // ================================================================= A producers
         const int ptid = tid - TCP_EPI;
         const int kq = ptid & 7;
