@@ -389,7 +389,7 @@ struct MaskEpi4 {
     const float* bias;
     const float* a0;
     static constexpr int kTcpEpiRegs = 104;  // persistent kernel: register re-allocation towards the epilogue warps (setmaxnreg)
-    static constexpr bool kRollPre = false;  // rolling prefetch of the next block (gemm_tcp.cuh ROLL): measured slower (0.96 vs 0.80 ms, loaded values spill at 72 registers)
+    static constexpr bool kRollPre = false;  // rolling prefetch of the next block (gemm_tcp.cuh ROLL): measured slower (0.96 vs 0.80 ms; 1.10 vs 0.77 ms with the register split)
     struct Pre {
         float2 er, ei;
     };
