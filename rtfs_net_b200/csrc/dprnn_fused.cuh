@@ -191,7 +191,10 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
             mbar_init(mma_done + s, 1);
         }
         mbar_init(acc_ready, 1);
-        for (int i = 0; i < 8 * 16; ++i) mbar_init(chunk_bar + i, 1);
+        fence_mbar_init();
+    }
+    if (tid >= 128 && tid < 256) {  // the 128 hand-off barriers, one per thread (a single thread took ~1.5 k cycles per tile)
+        mbar_init(chunk_bar + (tid - 128), 1);
         fence_mbar_init();
     }
     if (tid < DF_NP) {
@@ -386,24 +389,32 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
         // ---- h: warps q = 2 (columns 0-31) and q = 3 (columns 32-63); every step is independent, so each
         //      16-step batch is loaded, computed and stored as a block (no load waits behind a store)
         if (a.dbg != nullptr && tid == 64) a.dbg[(gridDim.x + blockIdx.x) * 16 + 2 * ly] = clock64();
-        if (q >= 2 && seq_on) {
+        // With two sequences per tile (time path: 2 x 125 frames) the warps of groups 2 and 3 have no sequence of their own:
+        // their h warps take every other 16-step block of sequences 0 and 1, so that h keeps up with the c-recurrence
+        // (h costs ~1.6 k cycles per block and warp, c ~0.8 k: the h warps were the long pole of every layer).
+        const bool h_help = a.nseq_tile == 2 && sw >= 2;
+        const int hs = h_help ? sw - 2 : sw;
+        if (q >= 2 && (seq_on || h_help)) {
             const int j = (q - 2) * 32 + lane;
             const float vr = __ldg(a.wc[ly] + 64 + j) * df_prescale<GATE>(), br = __ldg(a.bias[ly] + 64 + j);
             const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
             unsigned char* hb = hbuf + (j >> 2) * DF_LBO + 7 * 16 + (j & 3) * 4;
             const float* csj = cs + j;
-            const int p_end = ly == 3 ? p_lo + S : p_hi;  // the last layer also zeroes the 7 tail rows (conv-transpose padding)
-            const int m_lo = p_lo >> 4, m_hi = (p_end - 1) >> 4, m_chi = (p_hi - 1) >> 4;
+            const int hp_lo = hs * S, hp_hi = hp_lo + L;
+            const int p_end = ly == 3 ? hp_lo + S : hp_hi;  // the last layer also zeroes the 7 tail rows (conv-transpose padding)
+            const int m_lo = hp_lo >> 4, m_hi = (p_end - 1) >> 4, m_chi = (hp_hi - 1) >> 4;
+            const int par = a.nseq_tile == 2 ? (h_help ? 1 : 0) : -1;  // which blocks (in scan order) this group takes; -1: all
             for (int mm = m_lo; mm <= m_hi; ++mm) {
+                if (par >= 0 && ((mm - m_lo) & 1) != par) continue;
                 const int m = q == 2 ? mm : m_lo + m_hi - mm;  // follow the c-recurrence's block order
-                if (m <= m_chi) mbar_wait(chunk_bar + (sw * 2 + (q - 2)) * 16 + m, ly & 1);
-                const bool full = 16 * m >= p_lo && 16 * m + 16 <= p_hi;
+                if (m <= m_chi) mbar_wait(chunk_bar + (hs * 2 + (q - 2)) * 16 + m, ly & 1);
+                const bool full = 16 * m >= hp_lo && 16 * m + 16 <= hp_hi;
                 if (full) {
-                    if (ly == 0) df_hchunk<true, true, GATE>(tl, m, q == 3, p_lo, p_hi, p_end, vr, br, csj, hb);
-                    else df_hchunk<true, false, GATE>(tl, m, q == 3, p_lo, p_hi, p_end, vr, br, csj, hb);
+                    if (ly == 0) df_hchunk<true, true, GATE>(tl, m, q == 3, hp_lo, hp_hi, p_end, vr, br, csj, hb);
+                    else df_hchunk<true, false, GATE>(tl, m, q == 3, hp_lo, hp_hi, p_end, vr, br, csj, hb);
                 } else {
-                    if (ly == 0) df_hchunk<false, true, GATE>(tl, m, q == 3, p_lo, p_hi, p_end, vr, br, csj, hb);
-                    else df_hchunk<false, false, GATE>(tl, m, q == 3, p_lo, p_hi, p_end, vr, br, csj, hb);
+                    if (ly == 0) df_hchunk<false, true, GATE>(tl, m, q == 3, hp_lo, hp_hi, p_end, vr, br, csj, hb);
+                    else df_hchunk<false, false, GATE>(tl, m, q == 3, hp_lo, hp_hi, p_end, vr, br, csj, hb);
                 }
             }
         }
