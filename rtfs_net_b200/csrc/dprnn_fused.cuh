@@ -141,13 +141,14 @@ DEVINL void df_hchunk(uint32_t tl, int m, bool rev, int p_lo, int p_hi, int p_en
         for (int i = 0; i < 16; ++i) xp[i] = (FULL || (p0 + i >= p_lo && p0 + i < p_hi)) ? *reinterpret_cast<const float*>(hb + (p0 + i) * 16) : 0.f;
     }
     tmem_ld_wait();
+    const float brs = br * df_prescale<GATE>();
     float hv[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const float x = K4 ? __uint_as_float(ub[i]) : xp[i];
         const float cprev = rev ? cc[i + 2] : cc[i];
-        const float r = df_gate<GATE>(fmaf(vr, cprev, (__uint_as_float(ua[i]) + br) * df_prescale<GATE>()));
-        hv[i] = tf32r(fmaf(r, cc[i + 1] - x, x));
+        const float r = df_gate<GATE>(fmaf(vr, cprev, fmaf(__uint_as_float(ua[i]), df_prescale<GATE>(), brs)));
+        hv[i] = tf32r_fast(fmaf(r, cc[i + 1] - x, x));
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
     } while (0)
     DF_STAMP();
 
-    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    // barrier initialisation before anything is in flight: its release fence would otherwise wait for the loads below
     if (tid == 32) {
 #pragma unroll
         for (int s = 0; s < DF_NSTG; ++s) {
@@ -197,18 +198,48 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
         mbar_init(chunk_bar + (tid - 128), 1);
         fence_mbar_init();
     }
-    if (tid < DF_NP) {
-        const int p = tid;
-        const int s = p / S, l = p - s * S;
-        const int seqg = seq0 + s;
-        int off = -1;
-        if (s < a.nseq_tile && seqg < a.nseq_total) {
-            const int b = seqg / a.n_other, o = seqg - b * a.n_other;
-            const int t = a.time_path ? l : o, f = a.time_path ? o : l;
-            off = ((b * a.Tc + t) * a.Fc + f) * 64;
+
+    // ---- P0 loads first: every thread derives the global offsets of its 8 rows (positions p = 32 it + tid/16, channel quad
+    //      tid%16) incrementally and has them in flight while TMEM, the barriers and the tables below are set up
+    const int l16 = tid & 15, c = l16 * 4;
+    float4 v[8], plv[8];
+    int offs[8];
+    {
+        const float* src = a.first ? a.d1_pre : a.g_in;
+        const float* src2 = a.first ? a.pool : a.g_in;  // second stream only read when first
+        int p = tid >> 4;
+        int s = p / S, l = p - s * S;
+        int seqg = seq0 + s;
+        int b = seqg / a.n_other, o = seqg - b * a.n_other;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            int off = -1;
+            if (s < a.nseq_tile && seqg < a.nseq_total) {
+                const int t = a.time_path ? l : o, f = a.time_path ? o : l;
+                off = ((b * a.Tc + t) * a.Fc + f) * 64;
+            }
+            offs[it] = off;
+            v[it] = plv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (off >= 0) {
+                v[it] = ldg4(src + off + c);
+                if (a.first) plv[it] = ldg4(src2 + off + c);
+            }
+            if (l16 == 0) pos2off[p] = off;  // the position -> offset table of the epilogue
+            p += 32;
+            l += 32;
+            while (l >= S) {
+                l -= S;
+                ++s;
+                ++seqg;
+                if (++o == a.n_other) {
+                    o = 0;
+                    ++b;
+                }
+            }
         }
-        pos2off[p] = off;
     }
+
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
     if (a.first && tid >= 64 && tid < 68) {
         const int seqg = seq0 + (tid - 64);
         float mean = 0.f, rstd = 0.f;
@@ -244,22 +275,7 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
 
     // ---- P0: g -> LayerNorm over C -> n (tf32) into the slab; all 8 rows of a thread are in flight together
     {
-        const int l16 = tid & 15, c = l16 * 4;
         const float4 gm = ldg4(a.ln_gamma + c), be = ldg4(a.ln_beta + c);
-        float4 v[8], plv[8];
-        int offs[8];
-        const float* src = a.first ? a.d1_pre : a.g_in;
-        const float* src2 = a.first ? a.pool : a.g_in;  // second stream only read when first
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int p = it * 32 + (tid >> 4);
-            offs[it] = pos2off[p];
-            v[it] = plv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (offs[it] >= 0) {
-                v[it] = ldg4(src + offs[it] + c);
-                if (a.first) plv[it] = ldg4(src2 + offs[it] + c);
-            }
-        }
         if (a.first) {  // g = gLN(d1_pre) + pool, written out as the residual / next stage input
             const float4 gg = ldg4(a.gln.gamma + c), gb = ldg4(a.gln.beta + c);
 #pragma unroll
@@ -292,10 +308,10 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
             for (int o = 8; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
             const float rs = rsqrtf(qq * (1.f / 64.f) + RTFS_EPS);
             float4 n;
-            n.x = tf32r(dx * rs * gm.x + be.x);
-            n.y = tf32r(dy * rs * gm.y + be.y);
-            n.z = tf32r(dz * rs * gm.z + be.z);
-            n.w = tf32r(dw * rs * gm.w + be.w);
+            n.x = tf32r_fast(dx * rs * gm.x + be.x);
+            n.y = tf32r_fast(dy * rs * gm.y + be.y);
+            n.z = tf32r_fast(dz * rs * gm.z + be.z);
+            n.w = tf32r_fast(dw * rs * gm.w + be.w);
             if (offs[it] < 0) n = make_float4(0.f, 0.f, 0.f, 0.f);
             *reinterpret_cast<float4*>(hbuf + l16 * DF_LBO + (7 + p) * 16) = n;
         }
