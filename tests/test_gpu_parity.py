@@ -358,11 +358,18 @@ def test_kernel_generations_agree(golden_sd):
         "torch.save(out.cpu(), sys.argv[1])\n"
     ) % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden", "state_dict_rtfs.npz"))
     outs = {}
-    for tag, env in (("new", {}), ("old", {"RTFS_LEGACY_GEMM": "1", "RTFS_LEGACY_DW": "1", "RTFS_UNFUSED_CAF": "1", "RTFS_NO_VIDEO_GRAPH": "1"})):
+    variants = (
+        ("new", {}),
+        ("old", {"RTFS_LEGACY_GEMM": "1", "RTFS_LEGACY_DW": "1", "RTFS_UNFUSED_CAF": "1", "RTFS_NO_VIDEO_GRAPH": "1", "RTFS_LEGACY_FRONTEND": "1"}),
+        # second generation: tcgen05 GEMMs one tile per CTA, unfused RNN around them, scalar TF-AR conv, mma.sync attention convs
+        ("mid", {"RTFS_PERSIST_MASK": "0", "RTFS_UNFUSED_DPRNN": "1", "RTFS_SCALAR_TFAR": "1", "RTFS_LEGACY_ATT": "1", "RTFS_LEGACY_FRONTEND": "1"}),
+    )
+    for tag, env in variants:
         path = os.path.join(ROOT, "gpurun_out", f"gen_{tag}.pt")
         os.makedirs(os.path.dirname(path), exist_ok=True)
         subprocess.run([sys.executable, "-c", code, path], check=True, env={**os.environ, **env}, timeout=600)
         outs[tag] = torch.load(path)
-    e = rel_l2(outs["new"], outs["old"])
-    report(f"kernel generations new vs old rel_l2={e:.3e}")
-    assert e <= 1e-3
+    for tag in ("old", "mid"):
+        e = rel_l2(outs["new"], outs[tag])
+        report(f"kernel generations new vs {tag} rel_l2={e:.3e}")
+        assert e <= 1e-3
