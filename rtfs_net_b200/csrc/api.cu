@@ -457,15 +457,19 @@ int run_mhsa(const Ctx& c, const float* g_in, float* g_out) {
         aa.H = H;
         aa.tk_pad = ((d.Tc + AT_KR - 1) / AT_KR) * AT_KR;
         aa.scale = 1.f / sqrtf(4.f * 64.f);
-        const int smem = attn_smem_floats(aa.tk_pad) * 4;
+        static const bool qt32 = env_flag("RTFS_ATT_QT32");  // 32-query tiles (first schedule of this kernel)
+        const int qt = (qt32 || d.Tc <= 32) ? 32 : 64;
+        const int smem = attn_smem_floats(aa.tk_pad, qt) * 4;
         if (smem > 227 * 1024) return fail_msg("attention: too many frames for the shared-memory score tile");
-        static int cfg_smem = 0;
-        if (smem > cfg_smem) {
-            CKN(cudaFuncSetAttribute(attn_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            cfg_smem = smem;
+        static int cfg_smem[2] = {0, 0};
+        if (smem > cfg_smem[qt == 64]) {
+            if (qt == 64) CKN(cudaFuncSetAttribute(attn_core_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            else CKN(cudaFuncSetAttribute(attn_core_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            cfg_smem[qt == 64] = smem;
         }
         STAGE(RTFS_SG_ATT_CORE);
-        attn_core_kernel<<<dim3((d.Tc + AT_QT - 1) / AT_QT, d.B * H), 256, smem, c.st>>>(aa);
+        if (qt == 64) attn_core_kernel<64><<<dim3((d.Tc + 63) / 64, d.B * H), 512, smem, c.st>>>(aa);
+        else attn_core_kernel<32><<<dim3((d.Tc + 31) / 32, d.B * H), 256, smem, c.st>>>(aa);
         CK(cudaGetLastError());
     }
     if (att_tc) {

@@ -159,29 +159,37 @@ struct AttnArgs {
     float scale;        // 1/sqrt(E*F)
 };
 
-constexpr int AT_QT = 32, AT_KR = 32, AT_LDQ = 260, AT_LDV = 136;
+constexpr int AT_KR = 32, AT_LDQ = 260, AT_LDV = 136;
 // Q tile + score tile + one K/V chunk of AT_KR keys: 83 KB at 125 frames -> two CTAs per SM overlap each other's
 // load -> wait -> MMA rounds
-inline int attn_smem_floats(int tk_pad) {  // Q tile + score tile + max(one K chunk, two V chunks)
-    const int kv = AT_KR * AT_LDQ > 2 * AT_KR * AT_LDV ? AT_KR * AT_LDQ : 2 * AT_KR * AT_LDV;
-    return AT_QT * AT_LDQ + AT_QT * (tk_pad + 4) + kv;
+inline int attn_smem_floats(int tk_pad, int qt) {  // Q tile + score tile + max(one K chunk, two V chunks)
+    const int nb = qt == 64 ? 4 : 2;  // V chunk buffers (64-query tiles: one CTA per SM, room for a deeper ring and two K buffers)
+    const int kv = AT_KR * AT_LDQ > nb * AT_KR * AT_LDV ? AT_KR * AT_LDQ : nb * AT_KR * AT_LDV;
+    return qt * AT_LDQ + qt * (tk_pad + 4) + kv;
 }
 
-__global__ void __launch_bounds__(256, 2) attn_core_kernel(AttnArgs a) {
+// AT_QT queries per CTA (8 threads per query): K and V are re-read from L2 once per query tile, which is what bounds the
+// kernel (4 tiles of 32 queries at 125 frames = ~6 TB/s of L2 traffic), so 64-query tiles (512 threads, one CTA per SM)
+// halve it; the 32-query variant (two CTAs per SM) remains for short sequences.
+template <int AT_QT>
+__global__ void __launch_bounds__(AT_QT * 8, AT_QT == 32 ? 2 : 1) attn_core_kernel(AttnArgs a) {
+    constexpr int NT = AT_QT * 8, WM = AT_QT / 16;
+    constexpr int NB = AT_QT == 64 ? 4 : 2;      // V chunks in the ring (NB - 1 in flight)
+    constexpr bool KDB = NB * AT_KR * AT_LDV >= 2 * AT_KR * AT_LDQ;  // room for two K chunks: double-buffered QK^T phase
     extern __shared__ __align__(16) float sm[];
     const int SLD = a.tk_pad + 4;
     float* Qs = sm;                    // [32][260]
     float* Ss = Qs + AT_QT * AT_LDQ;   // [32][SLD]
     float* KV = Ss + AT_QT * SLD;      // K chunk [32][260]  /  V chunk [32][136]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-    const int wm = warp & 1, wn = warp >> 1;
+    const int wm = warp % WM, wn = warp / WM;
     const int bh = blockIdx.y, q0 = blockIdx.x * AT_QT;
     const int Tc = a.Tc;
     const float* Qg = a.q + (long long)bh * Tc * 256;
     const float* Kg = a.k + (long long)bh * Tc * 256;
     const float* Vg = a.v + (long long)bh * Tc * 1024;
 
-    for (int i = tid; i < AT_QT * 64; i += 256) {
+    for (int i = tid; i < AT_QT * 64; i += NT) {
         const int r = i >> 6, c4 = i & 63;
         const bool valid = (q0 + r) < Tc;
         cp_async16(Qs + r * AT_LDQ + c4 * 4, Qg + (long long)(valid ? q0 + r : 0) * 256 + c4 * 4, valid);
@@ -189,16 +197,31 @@ __global__ void __launch_bounds__(256, 2) attn_core_kernel(AttnArgs a) {
     cp_async_commit();
     const int nkc = a.tk_pad / AT_KR;
     // ---- S = scale * Q K^T : warp (wm, wn) -> 16 queries x 8 keys of the chunk
-    for (int kc = 0; kc < nkc; ++kc) {
-        for (int i = tid; i < AT_KR * 64; i += 256) {
+    auto issue_k = [&](int kc_) {
+        float* dstb = KV + (KDB ? (kc_ & 1) * (AT_KR * AT_LDQ) : 0);
+        for (int i = tid; i < AT_KR * 64; i += NT) {
             const int r = i >> 6, c4 = i & 63;
-            const int key = kc * AT_KR + r;
+            const int key = kc_ * AT_KR + r;
             const bool valid = key < Tc;
-            cp_async16(KV + r * AT_LDQ + c4 * 4, Kg + (long long)(valid ? key : 0) * 256 + c4 * 4, valid);
+            cp_async16(dstb + r * AT_LDQ + c4 * 4, Kg + (long long)(valid ? key : 0) * 256 + c4 * 4, valid);
         }
         cp_async_commit();
-        cp_async_wait<0>();
+    };
+    if (KDB) issue_k(0);
+    for (int kc = 0; kc < nkc; ++kc) {
+        if (KDB) {
+            if (kc + 1 < nkc) {
+                issue_k(kc + 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+        } else {
+            issue_k(kc);
+            cp_async_wait<0>();
+        }
         __syncthreads();
+        const float* Kb = KV + (KDB ? (kc & 1) * (AT_KR * AT_LDQ) : 0);
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 8
         for (int ks = 0; ks < 32; ++ks) {
@@ -208,7 +231,7 @@ __global__ void __launch_bounds__(256, 2) attn_core_kernel(AttnArgs a) {
             af[1] = __float_as_uint(p[8 * AT_LDQ]);
             af[2] = __float_as_uint(p[4]);
             af[3] = __float_as_uint(p[8 * AT_LDQ + 4]);
-            const float* q = KV + (wn * 8 + g) * AT_LDQ + ks * 8 + t;
+            const float* q = Kb + (wn * 8 + g) * AT_LDQ + ks * 8 + t;
             uint32_t bf[2] = {__float_as_uint(q[0]), __float_as_uint(q[4])};
             mma_tf32(acc, af, bf);
         }
@@ -228,8 +251,8 @@ __global__ void __launch_bounds__(256, 2) attn_core_kernel(AttnArgs a) {
     const int nst = 8 * nkc;
     auto issue_v = [&](int s_) {
         const int nc_ = s_ / nkc, kc_ = s_ - nc_ * nkc;
-        float* dstb = KV + (s_ & 1) * (AT_KR * AT_LDV);
-        for (int i = tid; i < AT_KR * 32; i += 256) {
+        float* dstb = KV + (s_ % NB) * (AT_KR * AT_LDV);
+        for (int i = tid; i < AT_KR * 32; i += NT) {
             const int r = i >> 5, c4 = i & 31;
             const int key = kc_ * AT_KR + r;
             const bool valid = key < Tc;
@@ -237,7 +260,11 @@ __global__ void __launch_bounds__(256, 2) attn_core_kernel(AttnArgs a) {
         }
         cp_async_commit();
     };
-    issue_v(0);
+#pragma unroll
+    for (int s_ = 0; s_ < NB - 1; ++s_) {
+        if (s_ < nst) issue_v(s_);
+        else cp_async_commit();
+    }
     // ---- softmax over keys (rows of Ss); padded keys get probability 0
     for (int r = warp * 4; r < warp * 4 + 4; ++r) {
         float* row = Ss + r * SLD;
@@ -260,14 +287,11 @@ __global__ void __launch_bounds__(256, 2) attn_core_kernel(AttnArgs a) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
         for (int kc = 0; kc < nkc; ++kc, ++st) {
-            if (st + 1 < nst) {
-                issue_v(st + 1);      // into the buffer chunk st-1 was read from (all warps passed the barrier below)
-                cp_async_wait<1>();   // chunk st has landed (this thread's pieces)
-            } else {
-                cp_async_wait<0>();
-            }
+            if (st + NB - 1 < nst) issue_v(st + NB - 1);  // into the buffer chunk st-1 was read from (all warps passed the barrier below)
+            else cp_async_commit();                       // (empty group: keeps the wait count uniform)
+            cp_async_wait<NB - 1>();                      // chunk st has landed (this thread's pieces)
             __syncthreads();          // everyone's pieces of chunk st (and, the first time, the softmax rows)
-            const float* Vb = KV + (st & 1) * (AT_KR * AT_LDV);
+            const float* Vb = KV + (st % NB) * (AT_KR * AT_LDV);
 #pragma unroll
             for (int ks = 0; ks < AT_KR / 8; ++ks) {
                 uint32_t af[4];
