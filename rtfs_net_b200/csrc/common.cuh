@@ -10,7 +10,10 @@
 #define RTFS_EPS 1e-5f
 
 // ------------------------------------------------------------------ TF32 tensor-core MMA (legacy path)
-DEVINL uint32_t f2tf32(float x) {
+// round-to-nearest (ties away) to TF32.  cvt.rna.tf32.f32 is emulated on sm_100a with three instructions (finite test +
+// IADD + LOP3); the two-instruction integer form gives the same bits for every finite input and +-inf.
+DEVINL uint32_t f2tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+DEVINL uint32_t f2tf32_cvt(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
