@@ -243,7 +243,7 @@ int run_bottleneck(const Ctx& c, const float* a0, float* a1, bool compute_stats)
     STAGE(RTFS_SG_BOTTLENECK);
     if (use_tc()) {
         StoreEpi4 ep{a1, 256, c.P[RTFS_P_BN_B]};
-        if (use_persistent(0)) CK((launch_gemm_tcp<256, 256, 4, 3, false, 4, 2, 512>(al, c.P[RTFS_P_BN_WI], ep, (int)(d.B * d.P), c.st)));
+        if (use_persistent(0)) CK((launch_gemm_tcp<256, 256, 3, 4, false, 4, 2, 512>(al, c.P[RTFS_P_BN_WI], ep, (int)(d.B * d.P), c.st)));
         else CK((launch_gemm_tc<256, 256, 3, 1, 4, 256>(al, c.P[RTFS_P_BN_WI], ep, (int)(d.B * d.P), c.st)));
     } else {
         StoreEpi ep{a1, 256, c.P[RTFS_P_BN_B]};
@@ -761,7 +761,7 @@ int run_mask(const Ctx& c, const float* refined, const float* a0, float* z) {
     STAGE(RTFS_SG_MASK);
     if (use_tc()) {
         MaskEpi4 ep{z, c.P[RTFS_P_MK_B], a0};
-        if (use_persistent(3)) CK((launch_gemm_tcp<256, 256, 4, 3, false, 4, 2, 512>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
+        if (use_persistent(3)) CK((launch_gemm_tcp<256, 256, 3, 4, false, 4, 2, 512>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
         else CK((launch_gemm_tc<256, 256, 3, 1, 4, 256>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
     } else {
         MaskEpi ep{z, c.P[RTFS_P_MK_B], a0};
