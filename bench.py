@@ -65,11 +65,16 @@ def measured_traffic(stage):
 
 
 def dprnn_flops(B):
-    """Algorithmic FLOPs of one fused dual-path RNN launch: per position of the (B, T', F') grid
-    unfold(8) o Linear 512 -> 256, three SRU layers 64 -> 256, ConvTranspose1d 8 x 64 -> 64 (2 FLOPs per MAC)."""
+    """Algorithmic FLOPs of one fused dual-path RNN launch, averaged over the two launches of a block pass (SURVEY.md
+    App. F): a path with O sequences of S positions runs the SRU stack on L = S - 7 unfolded steps, each step
+    unfold(8) o Linear 512 -> 256 (k = 4 gates), three layers 64 -> 192 (k = 3: identity highway) and its share of the
+    ConvTranspose1d 64 -> 64 x 8 taps; 2 FLOPs per MAC.  Frequency path: O = B*Tc, S = Fc; time path: O = B*Fc, S = Tc.
+    (= (933.9 + 3*87.6 + 233.5 + 989.9 + 3*92.8 + 247.5) / 2 MMAC per utterance at 2 s.)"""
     T = L // 128 + 1
     Tc, Fc = (T - 2) // 2 + 1, 64
-    return float(B * Tc * Fc) * 2.0 * (512 * 256 + 3 * 64 * 256 + 512 * 64)
+    per_step = 512 * 256 + 3 * 64 * 192 + 64 * 512
+    macs = B * Tc * (Fc - 7) * per_step + B * Fc * (Tc - 7) * per_step
+    return 2.0 * macs / 2.0
 
 
 def measured_tensor_peak():
@@ -102,14 +107,19 @@ def stage_bytes(B):
     T, Fq = L // 128 + 1, 129
     Tc, Fc = (T - 2) // 2 + 1, 64
     A, H, G = 4 * 256 * T * Fq * B, 4 * 64 * T * Fq * B, 4 * 64 * Tc * Fc * B
+    R = REPEATS
+    # residual conv: reads lec, d0 (2H), gec, ggc (2G), the block input x for the recomputed gateway (A), writes out (A)
+    # and -- passes 2..R-1 only -- reads the addend a1 (A).  The last pass has no addend; in the first pass (CAF fused in
+    # the epilogue) the addend IS x, read once.  RESID_OUT is timed over passes 2..R: average bytes of those launches.
+    resid_mid = (((R - 2) * 3 * A + 2 * A) / (R - 1) if R > 1 else 2 * A) + 2 * H + 2 * G
     return {
         "RTFS_SG_ENC_CONV": A, "RTFS_SG_BOTTLENECK": 2 * A, "RTFS_SG_GATE_PROJ": A + H, "RTFS_SG_DW_S1": 2 * H,
         "RTFS_SG_DW_S2_POOL": 2 * H + 2 * G, "RTFS_SG_DPRNN_FUSED": 3 * G, "RTFS_SG_DPRNN_PREP": 3 * G, "RTFS_SG_DPRNN_GEMM0": 5 * G,
         "RTFS_SG_DPRNN_SCAN": 5 * G, "RTFS_SG_DPRNN_GEMML": 4 * G, "RTFS_SG_DPRNN_CONVT": 3 * G,
         "RTFS_SG_ATT_QKV": 2.5 * G, "RTFS_SG_ATT_CORE": 2.5 * G, "RTFS_SG_ATT_PROJ": 3 * G,
         "RTFS_SG_TFAR_GLOBAL": 3.5 * G, "RTFS_SG_TFAR_LE0": 2 * H, "RTFS_SG_TFAR_CAT_GLOBAL": 5 * G,
-        "RTFS_SG_TFAR_CAT_LOCAL": 2 * H + 2 * G, "RTFS_SG_RESID_OUT": 3 * A + 2 * H + 2 * G, "RTFS_SG_CAF_APPLY": 3 * A,
-        "RTFS_SG_MASK": 3 * A, "RTFS_SG_DEC_GEMM": A * (1 + 18 / 256),
+        "RTFS_SG_TFAR_CAT_LOCAL": 2 * H + 2 * G, "RTFS_SG_RESID_OUT": resid_mid, "RTFS_SG_RESID_OUT_CAF": 2 * A + 2 * H + 2 * G,
+        "RTFS_SG_CAF_APPLY": 3 * A, "RTFS_SG_MASK": 3 * A, "RTFS_SG_DEC_GEMM": A * (1 + 18 / 256),
     }, (4 * A + 14 * H + 36 * G), ((6 + 4 * REPEATS) * A + 14 * REPEATS * H + 36 * REPEATS * G)
 
 
@@ -160,6 +170,56 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def config_block(world):
+    """The `config` object of both arms (identical keys so that the driver can compare them)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": BATCH, "repeats": REPEATS, "samples": L, "video_frames": TV,
+            "parallelism": f"dp{world} (batch shards, no collective)",
+            "l2": "no explicit flush: one step streams ~45 GB through a 7.3 GB working set >> 126 MB L2"}
+
+
+def check_against_golden(model, dev):
+    """One utterance of the committed reference golden case through the model before anything is timed: a bench number of
+    a build that no longer matches the reference is worthless."""
+    from conftest import load_case, rel_l2
+
+    case = load_case("rtfs4_b1_1s")
+    with torch.no_grad():
+        out = model(case["wav"].to(dev), case["lip"].to(dev))
+    err = rel_l2(out, case["out_ref_fp32"])
+    if not err <= 1e-3:
+        raise SystemExit(f"bench.py: golden check failed before timing (waveform rel-L2 {err:.3e} > 1e-3)")
+    return err
+
+
+def gpu_eager_rate(dev, n_utt, steps):
+    """What a user of the reference gets on this GPU today (BASELINE.md 4.6 / SURVEY.md 8d): the same forward as eager
+    PyTorch library ops (cuDNN / cuBLAS / ATen, TF32 matmuls as under set_float32_matmul_precision('high')) -- here the
+    oracle port run on the device, because the Python reference cannot travel to the GPU box.  Its SRU recurrence is a
+    Python loop over time steps (the upstream `sru` CUDA kernel is not available offline), which is stated in the line."""
+    from oracle import rtfs_oracle as O
+
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        sd = {k: v.to(dev) for k, v in load_state_dict().items()}
+        wav, lip = make_inputs(n_utt, 1)
+        wav, lip = wav.to(dev), lip.to(dev)
+        with torch.no_grad():
+            O.avnet_forward(sd, wav, lip, REPEATS)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                O.avnet_forward(sd, wav, lip, REPEATS)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    return n_utt / (ms * 1e-3), ms
+
+
 # ------------------------------------------------------------------------------- CPU arm
 def cpu_forward_rate(n_utt, steps, warmup):
     """utterances/s of the oracle port (CPU restatement of the reference forward) on the host cores."""
@@ -188,7 +248,9 @@ def run_reference(args, rank):
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "utterances/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "repeats": REPEATS, "samples": L, "video_frames": TV},
+        "config": config_block(args.gpus),
+        "note": f"each timed step is a forward over {n_utt} utterances (a bounded sample of the batch-32 step); ms_per_step is per "
+                f"{n_utt}-utterance step, value = utterances/s is directly comparable",
         "cpu_baseline": {"value": rate, "unit": "utterances/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -207,6 +269,7 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     model = build_model(load_state_dict(), REPEATS, dev)
+    golden_err = check_against_golden(model, dev)
     wav_h, lip_h = make_inputs(BATCH, 1000 + rank)
     wav_h, lip_h = wav_h.pin_memory(), lip_h.pin_memory()
     wav, lip = wav_h.to(dev), lip_h.to(dev)
@@ -302,8 +365,7 @@ def run_gpu(args):
     line = {
         "metric": METRIC, "value": value, "unit": "utterances/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 storage, tf32 tensor-core contractions", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "repeats": REPEATS, "samples": L, "video_frames": TV, "parallelism": f"dp{world} (batch shards, no collective)",
-                   "l2": "no explicit flush: one step streams ~45 GB through a 7.3 GB working set >> 126 MB L2"},
+        "config": config_block(world),
         "e2e": {"value": e2e, "unit": "utterances/s", "h2d_bytes_per_step": int(wav_h.numel() * 4 + lip_h.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4),
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": launches * K,
@@ -316,6 +378,15 @@ def run_gpu(args):
                              "frac": fwd_bytes / (ms_total / K * 1e-3) / 1e9 / peak},
         "stages": {k.replace("RTFS_SG_", "").lower(): {kk: round(vv, 4) for kk, vv in v.items()} for k, v in per_stage.items()},
     }
+    line["golden_check"] = {"case": "rtfs4_b1_1s (reference-generated fixture)", "waveform_rel_l2": golden_err, "bound": 1e-3}
+    if world == 1 and not args.no_eager:
+        try:
+            rate, ms = gpu_eager_rate(dev, BATCH, 2)
+            line["gpu_eager_baseline"] = {"value": rate, "unit": "utterances/s", "ms_per_step": ms, "batch": BATCH,
+                                          "what": "oracle port of the reference forward as eager PyTorch library ops on this GPU, TF32 matmuls; "
+                                                  "SRU recurrence = Python loop over time steps (upstream sru CUDA kernel not available offline)"}
+        except Exception as e:  # the baseline leg must never take the bench line down
+            line["gpu_eager_baseline"] = {"unavailable": repr(e)[:200]}
     if world == 1 and not args.no_cpu:
         rate, sec, cores = cpu_forward_rate(4, 1, 1)
         line["cpu_baseline"] = {"value": rate, "unit": "utterances/s", "cores": cores, "kind": "port",
@@ -330,6 +401,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

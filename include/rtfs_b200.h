@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RTFS_ABI_VERSION 5
+#define RTFS_ABI_VERSION 6
 #define RTFS_F 129
 #define RTFS_FC 64
 
@@ -110,6 +110,7 @@ enum rtfs_stage {
     RTFS_SG_TFAR_GLOBAL, RTFS_SG_TFAR_LE0, RTFS_SG_TFAR_CAT_GLOBAL, RTFS_SG_TFAR_CAT_LOCAL, RTFS_SG_RESID_OUT,
     RTFS_SG_CAF_VIDEO, RTFS_SG_CAF_APPLY, RTFS_SG_MASK, RTFS_SG_DEC_GEMM, RTFS_SG_DEC_ISTFT,
     RTFS_SG_DPRNN_FUSED, /* one launch per dual-path RNN (dprnn_fused.cuh) instead of PREP..CONVT */
+    RTFS_SG_RESID_OUT_CAF, /* residual conv of the first block pass with the CAF fusion in its epilogue (addend aliases x) */
     RTFS_SG_COUNT
 };
 

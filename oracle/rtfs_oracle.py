@@ -108,12 +108,12 @@ def stft_spec(wav, win=256, hop=128):
     TDAVNet/encoder.py:161-172.  wav (B,L) -> spec (B,2,T,F) with channel 0 = Re, 1 = Im."""
     B, L = wav.shape
     x = F.pad(wav[:, None, :], (win // 2, win // 2), mode="reflect")[:, 0]
-    frames = x.unfold(-1, win, hop) * hann_periodic(win, wav.dtype)  # (B,T,win)
+    frames = x.unfold(-1, win, hop) * hann_periodic(win, wav.dtype).to(wav.device)  # (B,T,win)
     n = torch.arange(win, dtype=torch.float64)
     f = torch.arange(win // 2 + 1, dtype=torch.float64)
     ang = 2.0 * math.pi * (n[:, None] * f[None, :] % win) / win
-    cosm = torch.cos(ang).to(wav.dtype)
-    sinm = (-torch.sin(ang)).to(wav.dtype)
+    cosm = torch.cos(ang).to(wav.dtype).to(wav.device)
+    sinm = (-torch.sin(ang)).to(wav.dtype).to(wav.device)
     return torch.stack([frames @ cosm, frames @ sinm], 1)  # (B,2,T,F)
 
 
@@ -138,12 +138,12 @@ def istft(re, im, length, win=256, hop=128):
     wgt = torch.full((Fq, 1), 2.0, dtype=torch.float64)
     wgt[0] = 1.0
     wgt[-1] = 1.0
-    cosm = (wgt * torch.cos(ang) / win).to(dt)
+    cosm = (wgt * torch.cos(ang) / win).to(dt).to(re.device)
     sinm = (-wgt * torch.sin(ang) / win)
     sinm[0] = 0.0  # imaginary parts of DC / Nyquist are ignored by a C2R transform
     sinm[-1] = 0.0
-    sinm = sinm.to(dt)
-    w = hann_periodic(win, dt)
+    sinm = sinm.to(dt).to(re.device)
+    w = hann_periodic(win, dt).to(re.device)
     frames = (re @ cosm + im @ sinm) * w  # (B,T,win)
     n_out = win + hop * (T - 1)
     y = re.new_zeros(B, n_out)

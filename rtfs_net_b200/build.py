@@ -44,8 +44,24 @@ def find_nvcc():
     return None
 
 
+def refresh_abi():
+    """Freeze the header's enum tables into rtfs_net_b200/_abi.py (so the package does not need include/ at run time)."""
+    import importlib
+
+    from . import _abi, _lib
+
+    if os.path.exists(_lib.HEADER):
+        before = (_abi.ABI_VERSION, list(_abi.PARAM_NAMES), list(_abi.WS_NAMES), list(_abi.STAT_NAMES), list(_abi.STAGE_NAMES), list(_abi.FUNCTIONS))
+        _lib.write_abi()
+        importlib.reload(_abi)
+        after = (_abi.ABI_VERSION, list(_abi.PARAM_NAMES), list(_abi.WS_NAMES), list(_abi.STAT_NAMES), list(_abi.STAGE_NAMES), list(_abi.FUNCTIONS))
+        if before != after:
+            importlib.reload(_lib)
+
+
 def build(force=False, verbose=False):
     """Compile the library if any source is newer than it.  Returns the library path."""
+    refresh_abi()
     if not force and up_to_date():
         return LIB_PATH
     nvcc = find_nvcc()

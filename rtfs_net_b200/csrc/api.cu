@@ -17,7 +17,6 @@
 #include "gemm.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tcp.cuh"
-#include "gateproj_wide.cuh"
 
 using namespace rtfs;
 
@@ -437,12 +436,9 @@ int run_mhsa(const Ctx& c, const float* g_in, float* g_out) {
         STAGE(RTFS_SG_ATT_QKV);
         CK((launch_att_conv_tc<96, 0>(aa, c.st)));
     } else {
-        static bool cfg = false;
         const int smem = rowblock_smem_floats<96>() * 4;
-        if (!cfg) {
-            CKN(cudaFuncSetAttribute(rowblock_ln_kernel<96, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            cfg = true;
-        }
+        static SmemCfg cfg;
+        CKN(ensure_smem(rowblock_ln_kernel<96, 0>, smem, cfg));
         STAGE(RTFS_SG_ATT_QKV);
         rowblock_ln_kernel<96, 0><<<d.B * d.Tc, 128, smem, c.st>>>(ra);
         CK(cudaGetLastError());
@@ -461,12 +457,9 @@ int run_mhsa(const Ctx& c, const float* g_in, float* g_out) {
         const int qt = (qt32 || d.Tc <= 32) ? 32 : 64;
         const int smem = attn_smem_floats(aa.tk_pad, qt) * 4;
         if (smem > 227 * 1024) return fail_msg("attention: too many frames for the shared-memory score tile");
-        static int cfg_smem[2] = {0, 0};
-        if (smem > cfg_smem[qt == 64]) {
-            if (qt == 64) CKN(cudaFuncSetAttribute(attn_core_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            else CKN(cudaFuncSetAttribute(attn_core_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            cfg_smem[qt == 64] = smem;
-        }
+        static SmemCfg cfg64, cfg32;
+        if (qt == 64) CKN(ensure_smem(attn_core_kernel<64>, smem, cfg64));
+        else CKN(ensure_smem(attn_core_kernel<32>, smem, cfg32));
         STAGE(RTFS_SG_ATT_CORE);
         if (qt == 64) attn_core_kernel<64><<<dim3((d.Tc + 63) / 64, d.B * H), 512, smem, c.st>>>(aa);
         else attn_core_kernel<32><<<dim3((d.Tc + 31) / 32, d.B * H), 256, smem, c.st>>>(aa);
@@ -503,12 +496,9 @@ int run_mhsa(const Ctx& c, const float* g_in, float* g_out) {
         rb.B = d.B;
         rb.Tc = d.Tc;
         rb.H = H;
-        static bool cfg = false;
         const int smem = rowblock_smem_floats<64>() * 4;
-        if (!cfg) {
-            CKN(cudaFuncSetAttribute(rowblock_ln_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            cfg = true;
-        }
+        static SmemCfg cfg;
+        CKN(ensure_smem(rowblock_ln_kernel<64, 1>, smem, cfg));
         STAGE(RTFS_SG_ATT_PROJ);
         rowblock_ln_kernel<64, 1><<<d.B * d.Tc, 128, smem, c.st>>>(rb);
         CK(cudaGetLastError());
@@ -535,10 +525,7 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out, boo
     {
         GateLoader al{x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], 256};
         STAGE(RTFS_SG_GATE_PROJ);
-        if (use_tc() && env_flag("RTFS_GATE_WIDE")) {  // 1024-thread lock-step variant: correct, but measured slower (0.58 vs 0.43 ms)
-            GwArgs ga{x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], P[RTFS_P_PJ_WI], P[RTFS_P_PJ_B], p_pre, c.stat(RTFS_ST_PJ), M, (int)d.P, d.B, 0};
-            CK(launch_gateproj_wide(ga, c.st));
-        } else if (use_tc()) {
+        if (use_tc()) {
             StatsEpi4 ep{p_pre, 64, P[RTFS_P_PJ_B], c.stat(RTFS_ST_PJ), (int)d.P, d.B};
             if (use_persistent(1)) CK((launch_gemm_tcp<64, 256, 4, 1, true, 4, 2, 512>(al, P[RTFS_P_PJ_WI], ep, M, c.st)));
                         else CK((launch_gemm_tc<64, 256, 4, 2, 2, 256>(al, P[RTFS_P_PJ_WI], ep, M, c.st)));
@@ -700,9 +687,9 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out, boo
         al.Tc = d.Tc;
         al.Fc = d.Fc;
         al.B = d.B;
-        STAGE(RTFS_SG_RESID_OUT);
+        STAGE(caf_fused ? RTFS_SG_RESID_OUT_CAF : RTFS_SG_RESID_OUT);
         if (caf_fused) {
-            if (addend != nullptr && addend != x) return -2;  // fused pass: the addend is the block input itself
+            if (addend != nullptr && addend != x) return fail_msg("block (fused CAF pass): the addend must be the block input itself");
             ResidOutCafEpi4 ep{out, P[RTFS_P_RC_B], x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], addend,
                                c.buf(RTFS_WS_VK), c.buf(RTFS_WS_ATT), P[RTFS_P_CAF_SK], P[RTFS_P_CAF_TK], P[RTFS_P_CAF_SV], P[RTFS_P_CAF_TV],
                                d.T, d.F, d.Tv, 0.f};
@@ -729,7 +716,7 @@ int run_caf(const Ctx& c, const float* audio, const float* video, const float* a
     CafApplyArgs aa{audio, addend, c.buf(RTFS_WS_VK), c.buf(RTFS_WS_ATT), P[RTFS_P_CAF_SK], P[RTFS_P_CAF_TK],
                     P[RTFS_P_CAF_SV], P[RTFS_P_CAF_TV], out, d.T, d.F, 256, d.Tv, d.B * d.P * 64};
     long long blocks = (aa.total4 + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
     STAGE(RTFS_SG_CAF_APPLY);
     caf_apply_kernel<<<(unsigned)blocks, 256, 0, c.st>>>(aa);
     CK(cudaGetLastError());
@@ -744,11 +731,8 @@ int run_caf_video(const Ctx& c, const float* video) {
                     c.buf(RTFS_WS_VK), c.buf(RTFS_WS_ATT), 256, d.Tv};
     const int smem = d.Tv * 256 * 4;
     if (smem > 200 * 1024) return fail_msg("CAF: too many video frames for the shared-memory softmax");
-    static int cfg_smem = 48 * 1024;
-    if (smem > cfg_smem) {
-        CKN(cudaFuncSetAttribute(caf_video_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        cfg_smem = smem;
-    }
+    static SmemCfg cfg;
+    if (smem > 48 * 1024) CKN(ensure_smem(caf_video_kernel, smem, cfg));
     STAGE(RTFS_SG_CAF_VIDEO);
     caf_video_kernel<<<d.B, 256, smem, c.st>>>(va);
     CK(cudaGetLastError());

@@ -276,14 +276,10 @@ template <int N, int MODE>
 inline cudaError_t launch_att_conv_tc(const AttConvArgs& a, cudaStream_t st) {
     auto kern = att_conv_ln_tc_kernel<N, MODE>;
     const int smem = att_conv_smem<N, MODE>();
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static SmemCfg cfg;  // per instantiation, per device
+    if (cudaError_t e = ensure_smem(kern, smem, cfg); e != cudaSuccess) return e;
     const int npairs = (a.nframes + 1) / 2;
-    const int grid = npairs < 148 * ac_ctas<MODE>() ? npairs : 148 * ac_ctas<MODE>();
+    const int grid = npairs < sm_count() * ac_ctas<MODE>() ? npairs : sm_count() * ac_ctas<MODE>();
     kern<<<grid, 128, smem, st>>>(a);
     return cudaGetLastError();
 }

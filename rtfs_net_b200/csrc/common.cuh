@@ -9,6 +9,39 @@
 #define DEVINL __device__ __forceinline__
 #define RTFS_EPS 1e-5f
 
+// ------------------------------------------------------------------ per-device launch configuration
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE attribute of a kernel: a process that runs models on
+// several devices must set it on each.  One cache per kernel instantiation (a `static SmemCfg` in its launch helper)
+// remembers the largest size configured on every device; racing threads at worst set the same attribute twice.
+namespace rtfs {
+constexpr int kMaxDevices = 64;
+struct SmemCfg {
+    int bytes[kMaxDevices] = {};
+};
+template <class K>
+inline cudaError_t ensure_smem(K kern, int smem, SmemCfg& cfg) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const bool cached = dev >= 0 && dev < kMaxDevices;
+    if (cached && cfg.bytes[dev] >= smem && cfg.bytes[dev] > 0) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess && cached) cfg.bytes[dev] = smem;
+    return e;
+}
+// SM count of the current device (148 on B200), cached per device; grids of the persistent kernels are sized from it
+inline int sm_count() {
+    static int cache[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < kMaxDevices && cache[dev] > 0) return cache[dev];
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (dev >= 0 && dev < kMaxDevices) cache[dev] = n;
+    return n;
+}
+}  // namespace rtfs
+
 // ------------------------------------------------------------------ TF32 tensor-core MMA (legacy path)
 // round-to-nearest (ties away) to TF32.  cvt.rna.tf32.f32 is emulated on sm_100a with three instructions (finite test +
 // IADD + LOP3); the two-instruction integer form gives the same bits for every finite input and +-inf.

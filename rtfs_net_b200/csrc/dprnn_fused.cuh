@@ -499,12 +499,8 @@ __global__ void __launch_bounds__(DF_NT, 1) dprnn_fused_kernel(DfArgs a) {
 
 template <int GATE>
 inline cudaError_t launch_dprnn_fused_g(const DfArgs& a, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(dprnn_fused_kernel<GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static SmemCfg cfg;  // per instantiation, per device
+    if (cudaError_t e = ensure_smem(dprnn_fused_kernel<GATE>, DF_SMEM, cfg); e != cudaSuccess) return e;
     const int tiles = (a.nseq_total + a.nseq_tile - 1) / a.nseq_tile;
     dprnn_fused_kernel<GATE><<<tiles, DF_NT, DF_SMEM, st>>>(a);
     return cudaGetLastError();

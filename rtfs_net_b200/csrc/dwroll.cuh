@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(NT, (NT > 256 ? 2 : 4)) dwroll_scalar_kernel(X
 
 // rows per CTA: as few segments as keep the 3-row halo re-read small while filling 148 SMs evenly
 inline int dr_rows_per_seg(int T, int B, int ctas_per_sm) {
-    const int slots = 148 * ctas_per_sm;
+    const int slots = sm_count() * ctas_per_sm;
     int best = T;
     double best_eff = 0.0;
     for (int nseg = 1; nseg <= 24 && nseg <= T; ++nseg) {
@@ -677,12 +677,8 @@ template <class XF, int NW, bool DUAL, int NT, int NR = DR_NR>
 inline cudaError_t launch_dwroll(const XF& xf, DrArgs<NW> a, int B, cudaStream_t st) {
     auto kern = dwroll_kernel<XF, NW, DUAL, NT, NR>;
     const int smem = NR * xf.slot_floats() * 4;
-    static int configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static SmemCfg cfg;  // per instantiation, per device
+    if (cudaError_t e = ensure_smem(kern, smem, cfg); e != cudaSuccess) return e;
     a.rows_per_seg = dr_rows(a.Ti, B);
     const int nseg = (a.Ti + a.rows_per_seg - 1) / a.rows_per_seg;
     kern<<<dim3(4 * nseg, B), NT, smem, st>>>(xf, a);
@@ -693,12 +689,8 @@ template <class XF, int NW, bool DUAL, int NT>
 inline cudaError_t launch_dwroll_scalar(const XF& xf, DrArgs<NW> a, int B, cudaStream_t st) {
     auto kern = dwroll_scalar_kernel<XF, NW, DUAL, NT>;
     const int smem = DR_NR * xf.slot_floats() * 4;
-    static int configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static SmemCfg cfg;  // per instantiation, per device
+    if (cudaError_t e = ensure_smem(kern, smem, cfg); e != cudaSuccess) return e;
     a.rows_per_seg = dr_rows(a.Ti, B);
     const int nseg = (a.Ti + a.rows_per_seg - 1) / a.rows_per_seg;
     kern<<<dim3(4 * nseg, B), NT, smem, st>>>(xf, a);

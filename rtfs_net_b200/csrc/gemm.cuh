@@ -635,12 +635,8 @@ template <int BN, int KTOT, bool PREC3, class AL, class EP>
 inline cudaError_t launch_gemm(const AL& al, const float* W, const EP& ep, int M, int N, cudaStream_t st) {
     auto kern = gemm_tf32_kernel<BN, KTOT, PREC3, AL, EP>;
     const size_t smem = sizeof(float) * gemm_smem_floats<BN>(AL::kExtra);
-    static bool configured = false;  // one flag per instantiation
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static SmemCfg cfg;  // per instantiation, per device
+    if (cudaError_t e = ensure_smem(kern, (int)smem, cfg); e != cudaSuccess) return e;
     const int nt = (N + BN - 1) / BN;
     const int mt = (M + GEMM_BM - 1) / GEMM_BM;
     kern<<<mt * nt, GEMM_THREADS, smem, st>>>(al, W, ep, M, N);

@@ -858,12 +858,8 @@ template <int BN, int NS, int MINB, class EP>
 inline cudaError_t launch_gemm_tc_unfold(const float* X, const float* Wimg, const EP& ep, int M, cudaStream_t st) {
     auto kern = gemm_tc_unfold_kernel<BN, NS, MINB, EP>;
     const int smem = tcu_smem_bytes<BN, NS>();
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static SmemCfg cfg;  // per instantiation, per device
+    if (cudaError_t e = ensure_smem(kern, smem, cfg); e != cudaSuccess) return e;
     kern<<<(M + TC_BM - 1) / TC_BM, TC_THREADS, smem, st>>>(X, Wimg, ep, M);
     return cudaGetLastError();
 }
@@ -872,12 +868,8 @@ template <int BN, int KTOT, int NS, int MINB, int PF, int NT, class AL, class EP
 inline cudaError_t launch_gemm_tc(const AL& al, const float* Wimg, const EP& ep, int M, cudaStream_t st) {
     auto kern = gemm_tc_kernel<BN, KTOT, NS, MINB, PF, NT, AL, EP>;
     const int smem = tc_smem_bytes<BN, NS, NT>(AL::kExtra);
-    static bool configured = false;  // one flag per instantiation
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static SmemCfg cfg;  // per instantiation, per device
+    if (cudaError_t e = ensure_smem(kern, smem, cfg); e != cudaSuccess) return e;
     kern<<<(M + TC_BM - 1) / TC_BM, NT, smem, st>>>(al, Wimg, ep, M);
     return cudaGetLastError();
 }

@@ -475,14 +475,10 @@ template <int BN, int KTOT, int NSA, int NSW, bool WRES, int PF, int ASYNC, int 
 inline cudaError_t launch_gemm_tcp(const AL& al, const float* Wimg, const EP& ep, int M, cudaStream_t st) {
     auto kern = gemm_tcp_kernel<BN, KTOT, NSA, NSW, WRES, PF, ASYNC, NPROD, AL, EP>;
     const int smem = tcp_smem_bytes<BN, KTOT, NSA, NSW, WRES>(AL::kExtra);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static SmemCfg cfg;  // per instantiation, per device
+    if (cudaError_t e = ensure_smem(kern, smem, cfg); e != cudaSuccess) return e;
     const int ntiles = (M + TC_BM - 1) / TC_BM;
-    const int grid = ntiles < 148 ? ntiles : 148;
+    const int grid = ntiles < sm_count() ? ntiles : sm_count();
     kern<<<grid, TCP_EPI + NPROD + 64, smem, st>>>(al, Wimg, ep, M, ntiles);
     return cudaGetLastError();
 }

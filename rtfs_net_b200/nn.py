@@ -157,6 +157,17 @@ class SRUCell(nn.Module):
         nn.init.uniform_(self.weight_c, -math.sqrt(3.0), math.sqrt(3.0))
         with torch.no_grad():
             self.weight_c.mul_(math.sqrt(0.5))
+        # upstream `sru` cells carry a `scale_x` buffer (only read when rescale=True, which SRU(...) does not enable:
+        # SURVEY.md App. B/C, from memory -- the package is not vendored).  It is registered so that checkpoints written
+        # here load strictly into the real package, and it is optional on load so that checkpoints without it load too.
+        self.register_buffer("scale_x", torch.zeros(1))
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        key = prefix + "scale_x"
+        if key not in state_dict:
+            state_dict = dict(state_dict)
+            state_dict[key] = self.scale_x.detach().clone()
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
 
 
 class SRU(nn.Module):
@@ -670,12 +681,18 @@ class _Runtime:
         (B,512,Tv) tensors: captured once per (shape, parameter version) into a CUDA graph and replayed.
         RTFS_NO_VIDEO_GRAPH=1 runs it eagerly."""
         rm = self.model.refinement_module
-        if os.environ.get("RTFS_NO_VIDEO_GRAPH"):
+        if os.environ.get("RTFS_NO_VIDEO_GRAPH") or torch.cuda.is_current_stream_capturing():
+            # (a forward that is itself being captured into a CUDA graph records the eager ops directly)
             return rm.video_net.get_block(0)(self.model.video_bottleneck(mouth)).contiguous()
         key = (str(mouth.device), tuple(mouth.shape), self._key)
-        ent = self._vgraph.get(key)
+        ent = self._vgraph.pop(key, None)
         if ent is None:
-            self._vgraph.clear()
+            # stale parameter versions can never be replayed again: drop them; keep a few shapes (e.g. the ragged last
+            # batch of an evaluation set alternating with the regular one) instead of re-capturing on every change
+            for k in [k for k in self._vgraph if k[2] != self._key]:
+                del self._vgraph[k]
+            while len(self._vgraph) >= 4:
+                del self._vgraph[next(iter(self._vgraph))]
             static_in = mouth.detach().clone()
             side = torch.cuda.Stream(device=mouth.device)
             side.wait_stream(torch.cuda.current_stream())
@@ -687,7 +704,7 @@ class _Runtime:
             with torch.cuda.graph(graph):
                 static_out = rm.video_net.get_block(0)(self.model.video_bottleneck(static_in)).contiguous()
             ent = (graph, static_in, static_out)
-            self._vgraph[key] = ent
+        self._vgraph[key] = ent  # (re-)insert last: the dict order is the LRU order
         graph, static_in, static_out = ent
         static_in.copy_(mouth)
         graph.replay()

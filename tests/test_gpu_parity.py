@@ -373,3 +373,114 @@ def test_kernel_generations_agree(golden_sd):
         e = rel_l2(outs["new"], outs[tag])
         report(f"kernel generations new vs {tag} rel_l2={e:.3e}")
         assert e <= 1e-3
+
+
+# ------------------------------------------------------------------------------- round 2: sizes and variety
+def test_forward_r6_vs_oracle(golden_sd, O):
+    """RTFS-Net-6 (BASELINE configs[2] geometry) against the CPU oracle."""
+    g = torch.Generator().manual_seed(41)
+    wav = 0.1 * torch.randn(2, 16000, generator=g)
+    lip = torch.rand(2, 512, 25, generator=g)
+    m = build_model(golden_sd, 6)
+    with torch.no_grad():
+        out = m(wav.cuda(), lip.cuda())
+        ref = O.avnet_forward(golden_sd, wav, lip, 6)
+    e = rel_l2(out, ref)
+    d = float((_sisdr_db(O, out, wav[:, None, :]) - _sisdr_db(O, ref, wav[:, None, :])).abs().max())
+    report(f"forward[1s b2 R6] waveform rel_l2={e:.3e} |dSI-SDR|={d:.2e} dB")
+    assert e <= 1e-3 and d <= 0.01
+
+
+def test_b32_eight_utterances_vs_oracle(golden_sd, O):
+    """BASELINE config 2 at size (B=32, 2 s, R=4): eight utterances spread over the batch against the CPU oracle, the
+    other 24 against the same utterances run as a second batch in a different order (batch independence)."""
+    g = torch.Generator().manual_seed(43)
+    wav = 0.1 * torch.randn(32, 32000, generator=g)
+    lip = torch.rand(32, 512, 50, generator=g)
+    m = build_model(golden_sd, 4)
+    picks = [0, 3, 9, 14, 17, 22, 27, 31]
+    with torch.no_grad():
+        out = m(wav.cuda(), lip.cuda()).cpu()
+        ref = O.avnet_forward(golden_sd, wav[picks], lip[picks], 4)
+        perm = torch.randperm(32, generator=g)
+        out_p = m(wav[perm].cuda(), lip[perm].cuda()).cpu()
+    errs = [rel_l2(out[i], ref[j]) for j, i in enumerate(picks)]
+    report("B=32 eight utterances vs oracle rel_l2 max=%.3e" % max(errs))
+    assert max(errs) <= 1e-3
+    e_perm = max(rel_l2(out_p[k], out[int(perm[k])]) for k in range(32))
+    report(f"B=32 permuted batch vs original rel_l2 max={e_perm:.3e}")
+    assert e_perm <= 1e-5  # same kernels, same per-utterance arithmetic: only fp64-atomic ordering differs
+
+
+def test_cfg4_at_size(golden_sd, O):
+    """BASELINE config 4 at size (B=64, 4 s, R=12; 29 GB workspace): two utterances of the batch against the CPU oracle."""
+    g = torch.Generator().manual_seed(47)
+    wav = 0.1 * torch.randn(64, 64000, generator=g)
+    lip = torch.rand(64, 512, 100, generator=g)
+    m = build_model(golden_sd, 12)
+    with torch.no_grad():
+        out = m(wav.cuda(), lip.cuda()).cpu()
+        ref = O.avnet_forward(golden_sd, wav[[7, 63]], lip[[7, 63]], 12)
+    assert out.shape == (64, 1, 64000) and torch.isfinite(out).all()
+    e = max(rel_l2(out[7], ref[0]), rel_l2(out[63], ref[1]))
+    d = float((_sisdr_db(O, out[[7, 63]], wav[[7, 63], None, :]) - _sisdr_db(O, ref, wav[[7, 63], None, :])).abs().max())
+    report(f"forward[cfg4 B=64 4s R12] two utterances vs oracle rel_l2={e:.3e} |dSI-SDR|={d:.2e} dB")
+    del m
+    torch.cuda.empty_cache()
+    assert e <= 1e-3 and d <= 0.01
+
+
+def test_non_default_stream_and_cuda_graph(golden_sd):
+    """The library launches on the caller's stream and never synchronises: the forward runs on a side stream and can be
+    captured into a CUDA graph; both reproduce the default-stream result bit for bit up to
+    the fp64 statistic atomics."""
+    case = load_case("rtfs4_b2_2s")
+    m = build_model(golden_sd, 4)
+    wav, lip = case["wav"].cuda(), case["lip"].cuda()
+    with torch.no_grad():
+        base = m(wav, lip).clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            out_side = m(wav, lip).clone()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        e_side = rel_l2(out_side, base)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out_graph = m(wav, lip)
+        out_graph.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        e_graph = rel_l2(out_graph, base)
+    report(f"side stream vs default rel_l2={e_side:.3e}; CUDA-graph replay vs default rel_l2={e_graph:.3e}")
+    assert e_side <= 1e-5 and e_graph <= 1e-5
+    assert rel_l2(out_graph, case["out_ref_fp32"]) <= 1e-3
+
+
+def test_trained_like_weight_scales(golden_sd, O):
+    """TF32 margin beyond random-init weights: every weight tensor gets its own gain (log-uniform in [0.5, 2]), biases
+    and norm offsets become non-zero, BatchNorm running statistics move away from (0, 1) -- the waveform must still be
+    within the 1e-3 bar of the fp32 oracle."""
+    g = torch.Generator().manual_seed(53)
+    sd = {}
+    for k, v in golden_sd.items():
+        v = v.clone()
+        if v.dtype.is_floating_point and "pos_enc" not in k and "scale_x" not in k:
+            if k.endswith("running_var"):
+                v = v * float(torch.empty(1).uniform_(0.5, 2.0, generator=g))
+            elif k.endswith("running_mean") or k.endswith(".bias") or k.endswith(".beta") or k.endswith("norm.bias"):
+                v = v + 0.05 * torch.randn(v.shape, generator=g)
+            else:
+                v = v * float(2.0 ** torch.empty(1).uniform_(-1.0, 1.0, generator=g))
+        sd[k] = v
+    wav = 0.1 * torch.randn(2, 16000, generator=g)
+    lip = torch.rand(2, 512, 25, generator=g)
+    m = build_model(sd, 4)
+    with torch.no_grad():
+        out = m(wav.cuda(), lip.cuda())
+        ref = O.avnet_forward(sd, wav, lip, 4)
+    e = rel_l2(out, ref)
+    d = float((_sisdr_db(O, out, wav[:, None, :]) - _sisdr_db(O, ref, wav[:, None, :])).abs().max())
+    report(f"forward[trained-like scales] waveform rel_l2={e:.3e} |dSI-SDR|={d:.2e} dB")
+    assert e <= 1e-3 and d <= 0.01
