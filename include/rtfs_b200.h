@@ -78,6 +78,18 @@ enum rtfs_param {
     RTFS_P_RF_FUSED, RTFS_P_RT_FUSED,
     RTFS_P_ENC_WI3, /* encoder conv, 3xTF32 split: image of [W_hi | W_hi | W_lo] (K = 96) */
     RTFS_P_AT_WQKVI, RTFS_P_AT_WOI, /* tcgen05 images of the attention conv weights: [16][96][4], [16][64][4] */
+    /* training only (may be NULL for inference): transposed images for the data-gradient GEMMs dX = dY * W, W'[N = K_fwd][K = N_fwd] */
+    RTFS_P_BN_WT,    /* [256][256] */
+    RTFS_P_PJ_WT,    /* [256][64]  */
+    RTFS_P_RC_WT,    /* [64][256]  */
+    RTFS_P_MK_WT,    /* [256][256], output channels (K) in NATURAL order (0..127 real, 128..255 imag) */
+    RTFS_P_RF_W0T, RTFS_P_RF_W1T, RTFS_P_RF_W2T, RTFS_P_RF_W3T, /* [512][256], [64][192] x3 */
+    RTFS_P_RF_CTWB,  /* [64 ci][tap*64 + co] = ConvTranspose1d weight[ci][co][tap] */
+    RTFS_P_RT_W0T, RTFS_P_RT_W1T, RTFS_P_RT_W2T, RTFS_P_RT_W3T,
+    RTFS_P_RT_CTWB,
+    RTFS_P_AT_WQKVT, /* [64][96] */
+    RTFS_P_AT_WOT,   /* [64][64] */
+    RTFS_P_DEC_WE,   /* [256][32]: decoder weight in the encoder-conv layout, k = (i*3+j)*2 + o (dz = conv2d(dy, W_dec)) */
     RTFS_P_COUNT
 };
 
@@ -90,6 +102,12 @@ enum rtfs_ws {
     RTFS_WS_Q, RTFS_WS_K, RTFS_WS_V,
     RTFS_WS_GE0, RTFS_WS_GG0, RTFS_WS_GE1, RTFS_WS_GG1, RTFS_WS_LE1, RTFS_WS_GEC, RTFS_WS_GGC,
     RTFS_WS_Q18, RTFS_WS_STATS, RTFS_WS_VK, RTFS_WS_ATT,
+    /* training tape of the two dual-path RNNs of a block pass (size 0 in the inference plan): LN output, and per SRU layer
+     * the gate pre-activations U, the cell states C and the layer outputs H (the last one zero-padded: HP) */
+    RTFS_WS_TF_N, RTFS_WS_TF_U0, RTFS_WS_TF_U1, RTFS_WS_TF_U2, RTFS_WS_TF_U3,
+    RTFS_WS_TF_C0, RTFS_WS_TF_C1, RTFS_WS_TF_C2, RTFS_WS_TF_C3, RTFS_WS_TF_H0, RTFS_WS_TF_H1, RTFS_WS_TF_H2, RTFS_WS_TF_HP,
+    RTFS_WS_TT_N, RTFS_WS_TT_U0, RTFS_WS_TT_U1, RTFS_WS_TT_U2, RTFS_WS_TT_U3,
+    RTFS_WS_TT_C0, RTFS_WS_TT_C1, RTFS_WS_TT_C2, RTFS_WS_TT_C3, RTFS_WS_TT_H0, RTFS_WS_TT_H1, RTFS_WS_TT_H2, RTFS_WS_TT_HP,
     RTFS_WS_COUNT
 };
 
@@ -112,6 +130,40 @@ enum rtfs_stage {
     RTFS_SG_DPRNN_FUSED, /* one launch per dual-path RNN (dprnn_fused.cuh) instead of PREP..CONVT */
     RTFS_SG_RESID_OUT_CAF, /* residual conv of the first block pass with the CAF fusion in its epilogue (addend aliases x) */
     RTFS_SG_COUNT
+};
+
+/* Training tape, global part (one per step; the per-pass parts follow, each laid out by rtfs_train_plan's pass offsets). */
+enum rtfs_tape {
+    RTFS_TP_SPEC = 0,  /* (B,T,F,2) STFT of the mixture */
+    RTFS_TP_A0, RTFS_TP_A1, /* encoder / bottleneck outputs (B,T,F,256) */
+    RTFS_TP_BLK0,      /* output of the first block pass = CAF audio input */
+    RTFS_TP_X,         /* block inputs of passes 1..R-1 (R-1 tensors back to back); X_1 = CAF(BLK0) + a1 */
+    RTFS_TP_REFINED,   /* output of the last pass */
+    RTFS_TP_M,         /* S^3 mask m = ReLU(conv) in natural channel order */
+    RTFS_TP_Z,         /* masked embedding (decoder input) */
+    RTFS_TP_Q18, RTFS_TP_VK, RTFS_TP_ATT,
+    RTFS_TP_CAFSUM,    /* doubles [256][2]: per-channel (sum, sum of squares) of BLK0 over this rank's batch */
+    RTFS_TP_PASS0,     /* first per-pass region; region i starts at offsets[RTFS_TP_PASS0] + i * pass_bytes */
+    RTFS_TP_COUNT
+};
+
+/* Backward scratch (gradients of activations; caller-provided, contents undefined between calls).  A = B*T*F*256 floats,
+ * H = B*T*F*64, G = B*Tc*Fc*64. */
+enum rtfs_bwd {
+    RTFS_BW_DA = 0, RTFS_BW_DB, /* ping/pong: gradient w.r.t. a block output / input (A) */
+    RTFS_BW_DA1,       /* accumulated gradient w.r.t. a1 (A) */
+    RTFS_BW_DM,        /* gradient w.r.t. the mask pre-activation; earlier dz (A) */
+    RTFS_BW_DA0,       /* gradient w.r.t. a0 (A) */
+    RTFS_BW_DSPEC,     /* (B,T,F,2) */
+    RTFS_BW_HE, RTFS_BW_HDE, RTFS_BW_HF0, RTFS_BW_HDF0, RTFS_BW_HT, /* H-sized */
+    RTFS_BW_GF1, RTFS_BW_GDF1, RTFS_BW_GT1, RTFS_BW_GT2, RTFS_BW_GT3, RTFS_BW_GT4, RTFS_BW_GT5, RTFS_BW_GD1N, RTFS_BW_GDD1N,
+    RTFS_BW_GDG3, RTFS_BW_GDG2, RTFS_BW_GDG1, RTFS_BW_GDG0, /* G-sized */
+    RTFS_BW_GA1, RTFS_BW_GA2, RTFS_BW_GA3, RTFS_BW_GS, RTFS_BW_GDP, RTFS_BW_GDQ, RTFS_BW_GDK, RTFS_BW_GDPRE, /* attention */
+    RTFS_BW_DZP, RTFS_BW_DHA, RTFS_BW_DHB, RTFS_BW_DU, RTFS_BW_DXIN, RTFS_BW_DXUNF, /* dual-path RNN */
+    RTFS_BW_RED,       /* doubles: gLN backward sums [32][B][2] */
+    RTFS_BW_DVK, RTFS_BW_DATT, /* (B,Tv,256) */
+    RTFS_BW_CSUM,      /* doubles [256][4]: CAF BatchNorm backward channel sums (this rank) */
+    RTFS_BW_COUNT
 };
 
 int rtfs_abi_version(void);
@@ -155,6 +207,55 @@ int rtfs_decoder_forward(const float* const* params, const float* z, float* wav_
  * for fusion_repeats = 1: wav (B,L), video = output of the video block (B,512,Tv) -> out (B,L).
  * repeats = audio_params.repeats (4 / 6 / 12). */
 int rtfs_avnet_forward(const float* const* params, const float* wav, const float* video, float* out, void* ws, int B, int L, int Tv, int repeats, void* stream);
+
+/* ---- training step (BASELINE configs[2]; reference call chain src/system/core.py:94-117 -> AVNet.forward -> loss.backward(),
+ * train.py:135-146).  The forward keeps a tape, the backward consumes it.
+ *
+ * rtfs_train_plan: sizes (bytes) of the tape and of the backward scratch for B utterances of L samples, Tv video frames and
+ * `repeats` block passes; tape_offsets[RTFS_TP_COUNT], bwd_offsets[RTFS_BW_COUNT] (bytes; may be NULL); *pass_bytes = size of
+ * one per-pass region, laid out like rtfs_ws_plan's workspace (query it with rtfs_train_pass_plan).  Returns the tape size. */
+long long rtfs_train_plan(int B, int L, int Tv, int repeats, long long* tape_offsets, long long* pass_bytes, long long* bwd_bytes, long long* bwd_offsets);
+long long rtfs_train_pass_plan(int B, int L, long long* offsets /* RTFS_WS_COUNT */);
+
+/* AVNet.forward in train() mode, split around the cross-rank reduction of the CAF BatchNorm statistics:
+ *   phase 0: encoder, bottleneck, first block pass, CAF video vectors, per-channel sums of the CAF audio input (RTFS_TP_CAFSUM)
+ *   -- the host forms the batch-statistics scale/shift of key_embed / value_embed (all-reducing the sums under SyncBatchNorm)
+ *      and stores them in the RTFS_P_CAF_SK/TK/SV/TV parameter slots --
+ *   phase 1: CAF, remaining passes, S^3 mask, decoder -> out (B,L).
+ * video = output of the video block (B,512,Tv). */
+int rtfs_avnet_train_forward(const float* const* params, const float* wav, const float* video, float* out, void* tape,
+                             int B, int L, int Tv, int repeats, int phase, void* stream);
+
+/* Backward of the above.  grads: RTFS_P_COUNT pointers to ZEROED buffers shaped like the parameter slots (NULL where no
+ * gradient is wanted / the slot is a derived image); gradients are accumulated into them.  Exceptions to "shaped like the
+ * slot": RTFS_P_MK_W / RTFS_P_MK_B gradients are written in NATURAL output-channel order.
+ *   phase 0: d_out (B,L) -> decoder, mask, passes R-1..1, CAF reductions (RTFS_BW_CSUM, d_video (B,512,Tv), CAF video-side grads)
+ *   -- the host all-reduces the channel sums under SyncBatchNorm and passes caf_mu / caf_c0 / caf_c1 ([256] each:
+ *      batch mean of the CAF input, sk*m1k + sv*m1v, sk*m2k*wk/sigk + sv*m2v*wv/sigv) --
+ *   phase 1: CAF input gradient, first block pass, bottleneck, encoder. */
+int rtfs_avnet_backward(const float* const* params, float* const* grads, const float* wav, const float* video, const float* d_out,
+                        float* d_video, const float* caf_mu, const float* caf_c0, const float* caf_c1, void* tape, void* scratch,
+                        int B, int L, int Tv, int repeats, int phase, void* stream);
+
+/* Module-level training entries (tests, partial use): the tape of a call is the per-pass region `pass_ws`. */
+int rtfs_block_train_forward(const float* const* params, const float* x, const float* addend, float* out, void* pass_ws, int B, int T, void* stream);
+int rtfs_block_backward(const float* const* params, float* const* grads, const float* x, const float* d_out, float* d_x,
+                        void* pass_ws, void* scratch, int B, int T, void* stream);
+int rtfs_dprnn_train_forward(const float* const* params, int which, const float* g_in, float* g_out, void* pass_ws, int B, int T, void* stream);
+int rtfs_dprnn_backward(const float* const* params, float* const* grads, int which, const float* g_in, const float* d_out, float* d_in,
+                        void* pass_ws, void* scratch, int B, int T, void* stream);
+int rtfs_mhsa_train_forward(const float* const* params, const float* g_in, float* g_out, void* pass_ws, int B, int T, void* stream);
+int rtfs_mhsa_backward(const float* const* params, float* const* grads, const float* g_in, const float* d_out, float* d_in,
+                       void* pass_ws, void* scratch, int B, int T, void* stream);
+
+/* PairwiseNegSDR("snr") for n_src = 1 (src/losses/matrix.py:22-53): loss[b] = -10 log10(sum t'^2 / (sum (e'-t')^2 + eps) + eps)
+ * with zero-meaned signals; d_est (may be NULL) = scale * d loss[b] / d est.  sums: B*5 doubles of scratch. */
+int rtfs_snr_loss(const float* est, const float* target, float* loss, float* d_est, double* sums, int B, int L, float scale, void* stream);
+
+/* clip_grad_norm_(max_norm) + torch.optim.AdamW step over flat buffers (src/system/optimizers.py:58-75, train.py:143):
+ * gnorm_sq (one double of scratch) receives sum(g^2) first; grad_scale multiplies the gradient (1/world after a sum all-reduce). */
+int rtfs_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int step, float max_norm, float grad_scale, double* gnorm_sq, void* stream);
 
 /* Number of kernels the last rtfs_avnet_forward on this thread launched (bench gpu_launches). */
 long long rtfs_last_launch_count(void);

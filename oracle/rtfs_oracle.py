@@ -52,8 +52,15 @@ def prelu(x, a):
     return torch.where(x >= 0, x, a.view(()) * x)
 
 
+BN_TRAIN = False  # True: BatchNorm layers normalise with the statistics of the batch (nn.Module.train() semantics)
+
+
 def batchnorm_eval(x, w, b, rm, rv, eps=1e-5):
     shape = (1, -1) + (1,) * (x.ndim - 2)
+    if BN_TRAIN:  # torch.nn.functional.batch_norm(training=True): biased variance over (batch, spatial)
+        dims = (0,) + tuple(range(2, x.ndim))
+        rm = x.mean(dim=dims)
+        rv = x.var(dim=dims, unbiased=False)
     return (x - rm.view(shape)) / torch.sqrt(rv.view(shape) + eps) * w.view(shape) + b.view(shape)
 
 
@@ -434,4 +441,14 @@ def neg_sisdr(est, target, eps=1e-8):
     proj = dot * t / energy
     noise = e - proj
     ratio = (proj**2).sum(-1) / ((noise**2).sum(-1) + eps)
+    return (-10.0 * torch.log10(ratio + eps))[:, 0]
+
+
+def neg_snr(est, target, eps=1e-8):
+    """PairwiseNegSDR('snr') for n_src = 1 (zero-mean, noise = est - target), /root/reference/src/losses/matrix.py:22-53;
+    the training loss of the reference (train.py:99).  est, target (B,1,L) -> (B,) negative SNR in dB."""
+    t = target - target.mean(dim=-1, keepdim=True)
+    e = est - est.mean(dim=-1, keepdim=True)
+    noise = e - t
+    ratio = (t**2).sum(-1) / ((noise**2).sum(-1) + eps)
     return (-10.0 * torch.log10(ratio + eps))[:, 0]

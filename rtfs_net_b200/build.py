@@ -51,10 +51,11 @@ def refresh_abi():
     from . import _abi, _lib
 
     if os.path.exists(_lib.HEADER):
-        before = (_abi.ABI_VERSION, list(_abi.PARAM_NAMES), list(_abi.WS_NAMES), list(_abi.STAT_NAMES), list(_abi.STAGE_NAMES), list(_abi.FUNCTIONS))
+        snap = lambda: {k: v for k, v in vars(_abi).items() if k.isupper()}
+        before = snap()
         _lib.write_abi()
         importlib.reload(_abi)
-        after = (_abi.ABI_VERSION, list(_abi.PARAM_NAMES), list(_abi.WS_NAMES), list(_abi.STAT_NAMES), list(_abi.STAGE_NAMES), list(_abi.FUNCTIONS))
+        after = snap()
         if before != after:
             importlib.reload(_lib)
 

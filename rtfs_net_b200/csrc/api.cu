@@ -120,7 +120,9 @@ struct Plan {
     long long total;
 };
 
-Plan make_plan(const Dims& d) {
+// train_pass: the per-pass region of the training tape -- no full-resolution 256-channel buffers (they live in the
+// global part of the tape), plus the dual-path RNN tape buffers
+Plan make_plan(const Dims& d, bool train_pass = false) {
     const long long B = d.B;
     const long long A = B * d.P * 256, H = B * d.P * 64, G = B * d.Pc * 64;
     long long sz[RTFS_WS_COUNT];
@@ -136,6 +138,20 @@ Plan make_plan(const Dims& d) {
     sz[RTFS_WS_Q18] = B * d.P * 18;
     sz[RTFS_WS_STATS] = (long long)RTFS_ST_COUNT * B * 2 * 2;  // doubles, counted in floats
     sz[RTFS_WS_VK] = sz[RTFS_WS_ATT] = B * (long long)(d.Tv > 0 ? d.Tv : 1) * 256;
+    for (int i = RTFS_WS_TF_N; i <= RTFS_WS_TT_HP; ++i) sz[i] = 0;
+    if (train_pass) {
+        sz[RTFS_WS_SPEC] = sz[RTFS_WS_A0] = sz[RTFS_WS_A1] = sz[RTFS_WS_XA] = sz[RTFS_WS_XB] = sz[RTFS_WS_Q18] = 0;
+        sz[RTFS_WS_VK] = sz[RTFS_WS_ATT] = 0;
+        for (int path = 0; path < 2; ++path) {
+            const int base = path == 0 ? RTFS_WS_TF_N : RTFS_WS_TT_N;
+            sz[base + 0] = G + 8 * 64;                                       // N
+            sz[base + 1] = B * d.Pc * 256 + 8 * 256;                         // U0
+            for (int l = 1; l <= 3; ++l) sz[base + 1 + l] = B * d.Pc * 192 + 8 * 192;  // U1..U3
+            for (int l = 0; l <= 3; ++l) sz[base + 5 + l] = G;               // C0..C3
+            for (int l = 0; l <= 2; ++l) sz[base + 9 + l] = G + 8 * 64;      // H0..H2
+            sz[base + 12] = B * (path == 0 ? hp_f : hp_t) * 64 + 8 * 64;     // HP
+        }
+    }
     Plan p;
     long long o = 0;
     for (int i = 0; i < RTFS_WS_COUNT; ++i) {
@@ -152,6 +168,7 @@ struct Ctx {
     Plan pl;
     char* ws;
     cudaStream_t st;
+    bool train = false;  // training forward: the dual-path RNNs run the taped kernel chain (train_api.cuh)
     float* buf(int i) const { return reinterpret_cast<float*>(ws + pl.off[i]); }
     double* stat(int slot) const { return reinterpret_cast<double*>(ws + pl.off[RTFS_WS_STATS]) + (long long)slot * d.B * 2; }
     GlnRef gln(int slot, int pg, int pb, long long n) const {
@@ -250,6 +267,8 @@ int run_bottleneck(const Ctx& c, const float* a0, float* a1, bool compute_stats)
     }
     return 0;
 }
+
+int run_dprnn_train(const Ctx& c, int which, bool first, const float* g_in, float* g_first, float* g_out);  // train_api.cuh
 
 // DualPathRNN.  first: g = gLN(d1_pre) + pool is formed here and written to g_first.
 int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_first, float* g_out) {
@@ -574,8 +593,13 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out, boo
         }
     }
     // S4-S9 global attention stack                                         tdanet.py:121
-    RUN(run_dprnn(c, 0, true, nullptr, g0, g1));
-    RUN(run_dprnn(c, 1, false, g1, nullptr, g2));
+    if (c.train) {
+        RUN(run_dprnn_train(c, 0, true, nullptr, g0, g1));
+        RUN(run_dprnn_train(c, 1, false, g1, nullptr, g2));
+    } else {
+        RUN(run_dprnn(c, 0, true, nullptr, g0, g1));
+        RUN(run_dprnn(c, 1, false, g1, nullptr, g2));
+    }
     RUN(run_mhsa(c, g2, g3));
     if (roll) {
         // S10-S12 TF-AR units                                                  tdanet.py:124-129, layers/fusion.py:54-69
@@ -739,12 +763,15 @@ int run_caf_video(const Ctx& c, const float* video) {
     return 0;
 }
 
-int run_mask(const Ctx& c, const float* refined, const float* a0, float* z) {
+int run_mask(const Ctx& c, const float* refined, const float* a0, float* z, float* m_out = nullptr) {
     const Dims& d = c.d;
     PreluLoader al{refined, c.P[RTFS_P_MK_A], 256};
     STAGE(RTFS_SG_MASK);
-    if (use_tc()) {
-        MaskEpi4 ep{z, c.P[RTFS_P_MK_B], a0};
+    if (m_out != nullptr) {  // training: the mask itself goes to the tape
+        MaskEpi4T<true> ep{z, c.P[RTFS_P_MK_B], a0, m_out};
+        CK((launch_gemm_tc<256, 256, 3, 1, 4, 256>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
+    } else if (use_tc()) {
+        MaskEpi4 ep{z, c.P[RTFS_P_MK_B], a0, nullptr};
         if (use_persistent(3)) CK((launch_gemm_tcp<256, 256, 3, 4, false, 4, 2, 512>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
         else CK((launch_gemm_tc<256, 256, 3, 1, 4, 256>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
     } else {
@@ -771,7 +798,7 @@ int run_decoder(const Ctx& c, const float* z, float* wav_out, int L) {
     return 0;
 }
 
-bool make_ctx(Ctx& c, const float* const* params, void* ws, int B, int T, int Tv, void* stream) {
+bool make_ctx(Ctx& c, const float* const* params, void* ws, int B, int T, int Tv, void* stream, bool train_pass = false) {
     if (params == nullptr || B < 1 || T < 16) {
         g_err = "bad arguments (params null, B < 1 or fewer than 16 frames)";
         return false;
@@ -782,7 +809,7 @@ bool make_ctx(Ctx& c, const float* const* params, void* ws, int B, int T, int Tv
         g_err = "batch too large for 32-bit row indexing (B*T*F*256 must be < 2^31 elements per call)";
         return false;
     }
-    c.pl = make_plan(c.d);
+    c.pl = make_plan(c.d, train_pass);
     c.ws = reinterpret_cast<char*>(ws);
     c.st = reinterpret_cast<cudaStream_t>(stream);
     return true;
@@ -908,3 +935,5 @@ int rtfs_avnet_forward(const float* const* params, const float* wav, const float
 }
 
 }  // extern "C"
+
+#include "train_api.cuh"

@@ -83,6 +83,7 @@ struct ScanArgs {
     int nseq, S, L, k;
     int out_stride, out_off;
     int zero_pad;  // also write 7 zero rows before and after the L valid rows (conv-transpose input)
+    float* cout = nullptr;  // training tape: the cell state c_t, rows seq*S + t (read again by sru_scan_bwd_kernel)
 };
 
 __global__ void __launch_bounds__(256) sru_scan_kernel(ScanArgs a) {
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(256) sru_scan_kernel(ScanArgs a) {
     const float* Ub = a.U + (long long)seq * a.S * a.ldu + col;
     const float* Xb = a.xin ? a.xin + (long long)seq * a.S * 64 + col : nullptr;
     float* Hb = a.hout + ((long long)seq * a.out_stride + a.out_off) * 64 + col;
+    float* Cb = a.cout ? a.cout + (long long)seq * a.S * 64 + col : nullptr;
     if (a.zero_pad) {
         for (int i = 0; i < 7; ++i) {
             Hb[(long long)(i - 7) * 64] = 0.f;
@@ -130,6 +132,7 @@ __global__ void __launch_bounds__(256) sru_scan_kernel(ScanArgs a) {
                 const float r = sigmoidf_fast(u2[i] + vr * c + br);
                 c = f * c + (1.f - f) * u0[i];
                 Hb[(long long)t * 64] = r * c + (1.f - r) * xp[i];
+                if (Cb) Cb[(long long)t * 64] = c;
             }
         }
     }

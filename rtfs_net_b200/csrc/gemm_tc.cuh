@@ -384,10 +384,12 @@ struct ResidOutCafEpi4 {
 
 // S^3 mask epilogue (mask_generator.py:67-99); GEMM columns interleaved on the host: col 2c = real-half
 // channel c, col 2c+1 = imag-half channel c+128 -> a float4 holds (re c, im c, re c+1, im c+1).
-struct MaskEpi4 {
+template <bool SAVE_M>
+struct MaskEpi4T {
     float* z;
     const float* bias;
     const float* a0;
+    float* m_out;  // SAVE_M (training tape): the mask m = ReLU(conv) in natural channel order (0..127 real | 128..255 imag)
     static constexpr int kTcpEpiRegs = 104;  // persistent kernel: register re-allocation towards the epilogue warps (setmaxnreg)
     static constexpr bool kRollPre = false;  // rolling prefetch of the next block (gemm_tcp.cuh ROLL): measured slower (0.96 vs 0.80 ms; 1.10 vs 0.77 ms with the register split)
     struct Pre {
@@ -409,12 +411,17 @@ struct MaskEpi4 {
         const float mr1 = fmaxf(v.z + bi.z, 0.f), mi1 = fmaxf(v.w + bi.w, 0.f);
         const long long o = (long long)row * 256 + (col >> 1);
         const float2 er = p.er, ei = p.ei;
+        if (SAVE_M) {
+            *reinterpret_cast<float2*>(m_out + o) = make_float2(mr0, mr1);
+            *reinterpret_cast<float2*>(m_out + o + 128) = make_float2(mi0, mi1);
+        }
         *reinterpret_cast<float2*>(z + o) = make_float2(er.x * mr0 - ei.x * mi0, er.y * mr1 - ei.y * mi1);
         *reinterpret_cast<float2*>(z + o + 128) = make_float2(er.x * mi0 + ei.x * mr0, er.y * mi1 + ei.y * mr1);
     }
     DEVINL void finish(float*) {}
     DEVINL void finish_group(float*, int, int, int) {}
 };
+using MaskEpi4 = MaskEpi4T<false>;
 
 // ConvTranspose1d-as-GEMM epilogue of the dual-path RNN (rnn_layers.py:153-160)
 struct ConvTEpi4 {

@@ -520,13 +520,27 @@ class _Runtime:
         self._ws = None
         self._ws_key = None
         self._vgraph = {}  # (device, shape, parameter key) -> (CUDAGraph, static input, static output) of the video block
+        self._train_bufs = None
 
     # ---------------------------------------------------------------- plumbing
-    def _check(self, *tensors):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()):
+    def _needs_train_path(self):
+        """train() mode (batch-statistics BatchNorm, dropout in the video block) or autograd through the parameters."""
+        return self.model.training or (torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()))
+
+    def train_buffers(self, B, L, Tv, R, device):
+        from .train import TrainBuffers
+
+        key = (B, L, Tv, R, str(device))
+        if self._train_bufs is None or self._train_bufs.key != key:
+            self._train_bufs = None  # release before allocating the new tape
+            self._train_bufs = TrainBuffers(B, L, Tv, R, device)
+        return self._train_bufs
+
+    def _check(self, *tensors, module_level=True):
+        if module_level and self._needs_train_path():
             raise NotImplementedError(
-                "rtfs_net_b200 implements the inference forward; call it under torch.no_grad() "
-                "(backward kernels are not part of this round)")
+                "module-level calls run the inference kernels: call them under torch.no_grad() in eval() mode "
+                "(training goes through AVNet.forward, which keeps the tape the backward kernels need)")
         for t in tensors:
             if t is None:
                 continue
@@ -534,8 +548,6 @@ class _Runtime:
                 raise RuntimeError("rtfs_net_b200 runs on CUDA tensors only (there is no CPU fallback)")
             if t.dtype != torch.float32:
                 raise TypeError("rtfs_net_b200 expects float32 tensors")
-        if self.model.training:
-            raise NotImplementedError("train-mode BatchNorm/Dropout statistics are not implemented; call model.eval()")
 
     def params(self, device):
         tensors = list(self.model.parameters()) + list(self.model.buffers())
@@ -710,13 +722,36 @@ class _Runtime:
         graph.replay()
         return static_out
 
+    @staticmethod
+    def _validate(wav, mouth):
+        """Shape limits of the kernels, checked up front with a readable message."""
+        if mouth is None:
+            raise ValueError("the RTFS-Net configurations are audio-visual: mouth_embedding (B,512,Tv) is required")
+        B, L = wav.shape
+        T = L // 128 + 1
+        if mouth.ndim != 3 or mouth.shape[0] != B or mouth.shape[1] != 512:
+            raise ValueError(f"mouth_embedding must be (B={B}, 512, Tv), got {tuple(mouth.shape)}")
+        if T < 16:
+            raise ValueError(f"mixture too short: {L} samples give {T} STFT frames, the dual-path RNN needs >= 16")
+        if not 1 <= mouth.shape[-1] <= 200:
+            raise ValueError(f"video length {mouth.shape[-1]} outside 1..200 frames (CAF soft-max tile in shared memory)")
+        if (T - 2) // 2 + 1 > 352:
+            raise ValueError(f"mixture too long for one call: {(T - 2) // 2 + 1} compressed frames > 352 (attention score tile in shared memory); split the utterance")
+        if B * T * 129 * 256 >= 2 ** 31:
+            raise ValueError(f"batch too large for one call: B*T*F*256 = {B * T * 129 * 256} must stay below 2^31 elements")
+
     # ---------------------------------------------------------------- whole forward (one C call)
     def forward(self, wav, mouth):
         if wav.ndim == 1:
             wav = wav[None]
         elif wav.ndim == 3:
             wav = wav[:, 0]
-        self._check(wav, mouth)
+        self._check(wav, mouth, module_level=False)
+        self._validate(wav, mouth)
+        if self._needs_train_path():
+            from .train import forward_train
+
+            return forward_train(self, wav, mouth)
         wav = wav.contiguous()
         B, L = wav.shape
         rm = self.model.refinement_module

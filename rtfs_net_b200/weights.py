@@ -18,10 +18,14 @@ CAF = "refinement_module.crossmodal_fusion.fusion_module.audio_lstm."
 
 
 def tf32_round(x: torch.Tensor) -> torch.Tensor:
-    """cvt.rna.tf32.f32: round to nearest (ties away from zero) to a 10-bit mantissa."""
+    """cvt.rna.tf32.f32: round to nearest (ties away from zero) to a 10-bit mantissa.  Under autograd the rounding is a
+    straight-through estimator (the gradient of the rounded image is the gradient of the fp32 master weight)."""
     i = x.detach().to(torch.float32).contiguous().view(torch.int32)
     i = (i + 0x1000) & -8192
-    return i.view(torch.float32)
+    r = i.view(torch.float32)
+    if x.requires_grad and torch.is_grad_enabled():
+        return x + (r - x).detach()
+    return r
 
 
 def umma_image(w: torch.Tensor) -> torch.Tensor:
@@ -63,9 +67,26 @@ def _tapmajor(w):
     return w.reshape(C, -1).t().contiguous()
 
 
-def prepare(sd, device):
-    """state_dict -> {slot name: tensor}"""
-    g = lambda k: sd[k].detach().to(device=device, dtype=torch.float32)
+# slots that only the training step reads (transposed images for the data-gradient GEMMs): NULL in the inference table
+TRAIN_ONLY = ("RTFS_P_BN_WT", "RTFS_P_PJ_WT", "RTFS_P_RC_WT", "RTFS_P_MK_WT", "RTFS_P_RF_W0T", "RTFS_P_RF_W1T", "RTFS_P_RF_W2T",
+              "RTFS_P_RF_W3T", "RTFS_P_RF_CTWB", "RTFS_P_RT_W0T", "RTFS_P_RT_W1T", "RTFS_P_RT_W2T", "RTFS_P_RT_W3T", "RTFS_P_RT_CTWB",
+              "RTFS_P_AT_WQKVT", "RTFS_P_AT_WOT", "RTFS_P_DEC_WE")
+# slots that are images / transposes of another slot: the backward returns no gradient for them (the base slot carries it)
+DERIVED = TRAIN_ONLY[:-1] + ("RTFS_P_BN_WI", "RTFS_P_PJ_WI", "RTFS_P_RC_WI", "RTFS_P_MK_WI", "RTFS_P_RF_WI0", "RTFS_P_RF_WI1", "RTFS_P_RF_WI2",
+                             "RTFS_P_RF_WI3", "RTFS_P_RF_CTWI", "RTFS_P_RT_WI0", "RTFS_P_RT_WI1", "RTFS_P_RT_WI2", "RTFS_P_RT_WI3", "RTFS_P_RT_CTWI",
+                             "RTFS_P_RF_FUSED", "RTFS_P_RT_FUSED", "RTFS_P_ENC_WI3", "RTFS_P_AT_WQKVI", "RTFS_P_AT_WOI", "RTFS_P_DEC_W",
+                             "RTFS_P_WINDOW", "RTFS_P_COSTAB", "RTFS_P_SINTAB", "RTFS_P_CAF_SK", "RTFS_P_CAF_TK", "RTFS_P_CAF_SV", "RTFS_P_CAF_TV")
+
+
+def prepare(sd, device, train=False):
+    """{reference key: tensor} -> {slot name: tensor}.  train=True: the inputs are the live parameters and every slot is a
+    differentiable function of them (reshapes / permutes / straight-through TF32 rounding), so autograd carries the slot
+    gradients the CUDA backward produces back to the parameters; the training-only transposed images are added and the
+    CAF BatchNorm scale / shift slots are plain buffers that the runtime fills from the batch statistics."""
+    if train:
+        g = lambda k: sd[k].to(device=device, dtype=torch.float32)
+    else:
+        g = lambda k: sd[k].detach().to(device=device, dtype=torch.float32)
     out = {}
     out["RTFS_P_WINDOW"] = torch.hann_window(256, periodic=True, dtype=torch.float32, device=device)
     k = torch.arange(256, dtype=torch.float64)
@@ -73,9 +94,7 @@ def prepare(sd, device):
     out["RTFS_P_SINTAB"] = torch.sin(2.0 * math.pi * k / 256).to(torch.float32).to(device)
 
     w = g("encoder.conv.full_layer.2.weight")  # (256,2,3,3) [co,ci,i,j] -> k = (i*3+j)*2+ci
-    enc = torch.zeros(256, 32, device=device)
-    enc[:, :18] = w.permute(0, 2, 3, 1).reshape(256, 18)
-    out["RTFS_P_ENC_W"] = enc
+    out["RTFS_P_ENC_W"] = torch.cat([w.permute(0, 2, 3, 1).reshape(256, 18), torch.zeros(256, 14, device=device)], 1)
 
     out["RTFS_P_BN_GAMMA"] = g("audio_bottleneck.full_layer.0.norm.weight")
     out["RTFS_P_BN_BETA"] = g("audio_bottleneck.full_layer.0.norm.bias")
@@ -163,6 +182,10 @@ def prepare(sd, device):
     out["RTFS_P_CAF_BEA"] = g(CAF + "attention_embed.full_layer.3.norm.bias")
     for name, s_slot, t_slot in (("key_embed", "SK", "TK"), ("value_embed", "SV", "TV")):
         q = CAF + name + ".full_layer."
+        if train:  # filled by the runtime (batch statistics in train(), running statistics in eval())
+            out[f"RTFS_P_CAF_{s_slot}"] = torch.zeros(256, device=device)
+            out[f"RTFS_P_CAF_{t_slot}"] = torch.zeros(256, device=device)
+            continue
         wdw = g(q + "2.weight").reshape(-1)
         inv = g(q + "3.weight") / torch.sqrt(g(q + "3.running_var") + 1e-5)
         out[f"RTFS_P_CAF_{s_slot}"] = wdw * inv
@@ -173,6 +196,21 @@ def prepare(sd, device):
     out["RTFS_P_MK_W"] = tf32_round(g("mask_generator.mask_generator.1.full_layer.2.weight").reshape(256, 256)[perm])
     out["RTFS_P_MK_B"] = g("mask_generator.mask_generator.1.full_layer.2.bias")[perm].contiguous()
     out["RTFS_P_DEC_W"] = g("decoder.decoder.weight").permute(1, 2, 3, 0).reshape(18, 256).contiguous()
+    if train:
+        # W'[N = K_fwd][K = N_fwd] images for dX = dY * W
+        out["RTFS_P_BN_WT"] = out["RTFS_P_BN_W"].t()
+        out["RTFS_P_PJ_WT"] = out["RTFS_P_PJ_W"].t()
+        out["RTFS_P_RC_WT"] = out["RTFS_P_RC_W"].t()
+        out["RTFS_P_MK_WT"] = tf32_round(g("mask_generator.mask_generator.1.full_layer.2.weight").reshape(256, 256)).t()  # natural order
+        for tag in ("RF", "RT"):
+            for l in range(4):
+                out[f"RTFS_P_{tag}_W{l}T"] = out[f"RTFS_P_{tag}_W{l}"].t()
+            q = BLK + f"globalatt.{0 if tag == 'RF' else 1}."
+            out[f"RTFS_P_{tag}_CTWB"] = tf32_round(g(q + "linear.weight").permute(0, 2, 1).reshape(64, 512))  # [ci][tap*64+co]
+        out["RTFS_P_AT_WQKVT"] = out["RTFS_P_AT_WQKV"].t()
+        out["RTFS_P_AT_WOT"] = out["RTFS_P_AT_WO"].t()
+        dw = torch.zeros(256, 32, device=device)
+        out["RTFS_P_DEC_WE"] = torch.cat([g("decoder.decoder.weight").permute(0, 2, 3, 1).reshape(256, 18), dw[:, 18:]], 1)  # k = (i*3+j)*2+o
 
     out["RTFS_P_AT_WQKVI"] = umma_image(out["RTFS_P_AT_WQKV"])
     out["RTFS_P_AT_WOI"] = umma_image(out["RTFS_P_AT_WO"])
@@ -188,19 +226,20 @@ def prepare(sd, device):
         out[f"RTFS_P_{tag}_FUSED"] = dprnn_fused_image(
             out[f"RTFS_P_{tag}_W0"], [out[f"RTFS_P_{tag}_W{l}"] for l in (1, 2, 3)], out[f"RTFS_P_{tag}_CTW"])
 
-    missing = [n for n in _lib.PARAM_NAMES if n not in out]
+    missing = [n for n in _lib.PARAM_NAMES if n not in out and not (n in TRAIN_ONLY and not train)]
     if missing:
         raise RuntimeError(f"unprepared parameter slots: {missing}")
-    return {n: out[n].contiguous() for n in _lib.PARAM_NAMES}
+    return {n: (out[n].contiguous() if n in out else None) for n in _lib.PARAM_NAMES}
 
 
 class PackedParams:
     """The pointer table passed as `params` to every C-ABI call (keeps the tensors alive)."""
 
-    def __init__(self, sd, device):
+    def __init__(self, sd, device, train=False):
         self.device = torch.device(device)
-        self.tensors = prepare(sd, self.device)
-        self.table = (ctypes.c_void_p * len(_lib.PARAM_NAMES))(*[self.tensors[n].data_ptr() for n in _lib.PARAM_NAMES])
+        self.tensors = prepare(sd, self.device, train)
+        self.table = (ctypes.c_void_p * len(_lib.PARAM_NAMES))(
+            *[(self.tensors[n].data_ptr() if self.tensors[n] is not None else None) for n in _lib.PARAM_NAMES])
 
     @property
     def ptr(self):

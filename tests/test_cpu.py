@@ -139,8 +139,10 @@ def test_no_cpu_fallback(golden_sd):
     with torch.no_grad():
         with pytest.raises(RuntimeError):
             m(torch.zeros(1, 32000), torch.zeros(1, 512, 50))
-    with pytest.raises(NotImplementedError):  # autograd: backward kernels are not part of this round
+    with pytest.raises(RuntimeError):  # autograd / train(): the training path is CUDA-only as well
         m(torch.zeros(1, 32000), torch.zeros(1, 512, 50))
+    with pytest.raises(NotImplementedError):  # module-level calls are inference entries
+        m.encoder(torch.zeros(1, 32000))
 
 
 def test_tf32_round():
@@ -209,13 +211,15 @@ def test_workspace_plan_is_consistent():
     total, offs = _lib.ws_plan(2, 32000, 50)
     order = [offs[n] for n in _lib.WS_NAMES]
     assert order == sorted(order) and order[0] == 0 and all(o % 256 == 0 for o in order)
-    assert total > order[-1]
+    assert total >= order[-1] and total > offs["RTFS_WS_ATT"]
     T, Fq = 251, 129
     assert offs["RTFS_WS_A1"] - offs["RTFS_WS_A0"] >= 2 * T * Fq * 256 * 4
     # the buffers whose size depends on the video length come last, so module-level calls that
     # do not know Tv address the same offsets
     _, offs0 = _lib.ws_plan(2, 32000, 0)
-    assert all(offs0[n] == offs[n] for n in _lib.WS_NAMES if n not in ("RTFS_WS_ATT",))
+    tape = lambda n: n.startswith("RTFS_WS_TF_") or n.startswith("RTFS_WS_TT_")  # training tape: empty in the inference plan
+    assert all(offs0[n] == offs[n] for n in _lib.WS_NAMES if n not in ("RTFS_WS_ATT",) and not tape(n))
+    assert len({offs[n] for n in _lib.WS_NAMES if tape(n)}) == 1
     big, _ = _lib.ws_plan(32, 32000, 50)
     assert big < 12e9
 
@@ -282,8 +286,9 @@ def test_abi_tables_frozen_in_package_match_header():
     """rtfs_net_b200/_abi.py (what the installed package uses) is in sync with include/rtfs_b200.h."""
     from rtfs_net_b200 import _abi, _lib
 
-    params, ws, stats, stages, fns, ver = _lib.header_tables()
-    assert (_abi.ABI_VERSION, _abi.PARAM_NAMES, _abi.WS_NAMES, _abi.STAT_NAMES, _abi.STAGE_NAMES, _abi.FUNCTIONS) == (ver, params, ws, stats, stages, fns)
+    params, ws, stats, stages, fns, ver, tape, bwd = _lib.header_tables()
+    assert (_abi.ABI_VERSION, _abi.PARAM_NAMES, _abi.WS_NAMES, _abi.STAT_NAMES, _abi.STAGE_NAMES, _abi.FUNCTIONS, _abi.TAPE_NAMES, _abi.BWD_NAMES) == (
+        ver, params, ws, stats, stages, fns, tape, bwd)
 
 
 def test_sru_scale_x_optional_on_load(golden_sd):

@@ -306,7 +306,10 @@ def test_errors(model):
         with torch.no_grad():
             model.encoder(torch.zeros(1, 32000))  # CPU tensor: no fallback
     with pytest.raises(NotImplementedError):
-        model(torch.zeros(1, 32000, device="cuda"), torch.zeros(1, 512, 50, device="cuda"))  # autograd enabled
+        model.encoder(torch.zeros(1, 32000, device="cuda"))  # module-level entries are inference-only: autograd is enabled here
+    with pytest.raises(ValueError):
+        with torch.no_grad():
+            model(torch.zeros(1, 1000, device="cuda"), torch.zeros(1, 512, 50, device="cuda"))  # too short: validated up front
 
 
 def test_forward_4s_vs_oracle(golden_sd, O):
