@@ -220,6 +220,65 @@ def gpu_eager_rate(dev, n_utt, steps):
     return n_utt / (ms * 1e-3), ms
 
 
+def train_step_block(dev, rank, world, steps=5, warmup=2):
+    """BASELINE configs[2]: RTFS-Net-6 training step, batch 16 per GPU, SNR loss, gradient all-reduce (NCCL when world > 1),
+    clip + AdamW -- forward with tape, hand-written CUDA backward, one flat all-reduce, fused optimizer kernel
+    (rtfs_net_b200/train.py).  Returns the `train_step` object of the JSON line (rank 0) or None."""
+    from conftest import audionet_conf
+    from rtfs_net_b200 import AVNet, _lib, shard
+    from rtfs_net_b200.train import Trainer
+
+    R, B = 6, 16
+    model = AVNet(print_macs=False, **audionet_conf(R))
+    model.load_state_dict(load_state_dict(), strict=True)
+    model = model.to(dev)
+    if world > 1:  # train.py:145 sync_batchnorm=True
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+    tr = Trainer(model, lr=1e-3, weight_decay=0.1, clip=5.0)
+    g = torch.Generator().manual_seed(2000 + rank)
+    tgt = (0.1 * torch.randn(B, 1, L, generator=g)).to(dev)
+    wav = (tgt[:, 0] + 0.1 * torch.randn(B, L, generator=g).to(dev))
+    lip = torch.rand(B, 512, TV, generator=g).to(dev)
+    losses = []
+    for _ in range(warmup):
+        losses.append(float(tr.step(wav, tgt, lip)))
+    torch.cuda.synchronize()
+    shard.barrier()
+    evs = []
+    launches0 = 0
+    for _ in range(steps):
+        ev = []
+        losses.append(tr.step(wav, tgt, lip, events=ev))
+        evs.append(ev)
+    torch.cuda.synchronize()
+    shard.barrier()
+    total = evs[0][0].elapsed_time(evs[-1][3])
+    fwd = sum(e[0].elapsed_time(e[1]) for e in evs) / steps
+    bwd = sum(e[1].elapsed_time(e[2]) for e in evs) / steps
+    opt = sum(e[2].elapsed_time(e[3]) for e in evs) / steps
+    total = shard.max_over_ranks(total, dev)
+    losses = [float(x) for x in losses]
+    peak_mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    grad_bytes = int(tr.flat_g.numel() * 4)
+    del tr, model
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    T, Fq = L // 128 + 1, 129
+    Tc, Fc = (T - 2) // 2 + 1, 64
+    A, H, G = 4 * 256 * T * Fq * B, 4 * 64 * T * Fq * B, 4 * 64 * Tc * Fc * B
+    fwd_bytes = (6 + 4 * R) * A + 14 * R * H + 36 * R * G
+    ms = total / steps
+    peak, _ = measured_peaks()
+    return {"config": f"RTFSNet {R}-layer training step (SNR loss + grad allreduce), batch {B}/GPU, 2 s @ 16 kHz synthetic, dp{world}",
+            "ms_per_step": ms, "utterances_per_s": B * world / (ms * 1e-3), "forward_loss_ms": fwd, "backward_ms": bwd, "allreduce_optimizer_ms": opt,
+            "steps": steps, "warmup": warmup, "loss_first": losses[0], "loss_last": losses[-1],
+            "allreduce": {"backend": "nccl" if world > 1 else None, "bytes_per_step": grad_bytes, "what": "one sum all-reduce of the flat fp32 gradient"},
+            "algorithmic_bytes": {"what": "3 x forward bytes ((6+4R)A + 14RH + 36RG): forward + data-gradient + weight-gradient passes", "bytes": 3 * fwd_bytes,
+                                  "achieved_gbps": 3 * fwd_bytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": 3 * fwd_bytes / (ms * 1e-3) / 1e9 / peak},
+            "peak_memory_gib": peak_mem, "sync_batchnorm": world > 1}
+
+
 # ------------------------------------------------------------------------------- CPU arm
 def cpu_forward_rate(n_utt, steps, warmup):
     """utterances/s of the oracle port (CPU restatement of the reference forward) on the host cores."""
@@ -324,6 +383,14 @@ def run_gpu(args):
 
     ms_total = shard.max_over_ranks(ms_total, dev)
     ms_e2e = shard.max_over_ranks(ms_e2e, dev)
+    train_block = None
+    if not args.no_train:
+        del model
+        torch.cuda.empty_cache()
+        try:
+            train_block = train_step_block(dev, rank, world)
+        except Exception as e:  # the extra block must never take the headline line down
+            train_block = {"unavailable": repr(e)[:300]}
     if rank != 0:
         return
     n_utt = BATCH * world * K
@@ -378,6 +445,8 @@ def run_gpu(args):
                              "frac": fwd_bytes / (ms_total / K * 1e-3) / 1e9 / peak},
         "stages": {k.replace("RTFS_SG_", "").lower(): {kk: round(vv, 4) for kk, vv in v.items()} for k, v in per_stage.items()},
     }
+    if train_block is not None:
+        line["train_step"] = train_block
     line["golden_check"] = {"case": "rtfs4_b1_1s (reference-generated fixture)", "waveform_rel_l2": golden_err, "bound": 1e-3}
     if world == 1 and not args.no_eager:
         try:
@@ -402,6 +471,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the train_step block (RTFS-Net-6 training step, batch 16 per GPU)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -265,7 +265,7 @@ int run_dprnn_bwd(const TrainCtx& t, const Ctx& c, int which, const float* g_in,
         StoreEpi ep{dhA, 64, nullptr};
         CK((launch_gemm<64, 512, false>(al, t.P[baset + 4], ep, Mp, 64, t.st)));
         PlainLoader xl{tp.hp, 64, 512}, yl{dzp, 64, 64};
-        CK((launch_wgrad<true>(xl, yl, t.grad(base + 14), 512, Mp, 64, 512, t.st)));
+        CK((launch_wgrad<false>(xl, yl, t.grad(base + 14), 512, Mp, 64, 512, t.st)));
         RUN(colsum<64>(t, dzp, Mp, t.grad(base + 15)));
     }
     // 3. SRU layers 3..1 (identity highway)
@@ -277,7 +277,7 @@ int run_dprnn_bwd(const TrainCtx& t, const Ctx& c, int which, const float* g_in,
         sru_scan_bwd_kernel<<<(nseq + 3) / 4, 256, 0, t.st>>>(sa);
         CK(cudaGetLastError());
         PlainLoader xl{tp.h[l - 1], 64, 64}, yl{dU, 192, 192};
-        CK((launch_wgrad<true>(xl, yl, t.grad(pw), 64, M, 192, 64, t.st)));
+        CK((launch_wgrad<false>(xl, yl, t.grad(pw), 64, M, 192, 64, t.st)));
         float* dprev = dh == dhA ? dhB : dhA;
         PlainLoader al{dU, 192, 192};
         AddEpi ep{dprev, 64, dxin};
@@ -292,7 +292,7 @@ int run_dprnn_bwd(const TrainCtx& t, const Ctx& c, int which, const float* g_in,
         sru_scan_bwd_kernel<<<(nseq + 3) / 4, 256, 0, t.st>>>(sa);
         CK(cudaGetLastError());
         PlainLoader xl{tp.n, 64, 512}, yl{dU, 256, 256};
-        CK((launch_wgrad<true>(xl, yl, t.grad(pw), 512, M, 256, 512, t.st)));
+        CK((launch_wgrad<false>(xl, yl, t.grad(pw), 512, M, 256, 512, t.st)));
         PlainLoader al{dU, 256, 256};
         StoreEpi ep{dxunf, 512, nullptr};
         CK((launch_gemm<128, 256, false>(al, t.P[baset + 0], ep, M, 512, t.st)));
@@ -335,7 +335,7 @@ int run_mhsa_bwd(const TrainCtx& t, const Ctx& c, const float* g_in, const float
         StoreEpi ep{ga2, 64, nullptr};
         CK((launch_gemm<64, 64, false>(al, t.P[RTFS_P_AT_WOT], ep, M, 64, t.st)));
         PlainLoader xl{ao, 64, 64}, yl{ga1, 64, 64};
-        CK((launch_wgrad<true>(xl, yl, t.grad(RTFS_P_AT_WO), 64, M, 64, 64, t.st)));
+        CK((launch_wgrad<false>(xl, yl, t.grad(RTFS_P_AT_WO), 64, M, 64, 64, t.st)));
         RUN(colsum<64>(t, ga1, M, t.grad(RTFS_P_AT_BO)));
     }
     // 2. per-head token rows of dO ; scores and their gradients
@@ -363,16 +363,16 @@ int run_mhsa_bwd(const TrainCtx& t, const Ctx& c, const float* g_in, const float
     {
         AttQkvBwdArgs a{g_in, t.P[RTFS_P_AT_WQKV], t.P[RTFS_P_AT_BQKV], t.P[RTFS_P_AT_SLOPE], t.P[RTFS_P_AT_GAMMA], gdq, gdk, ga2, gdpre,
                         t.grad(RTFS_P_AT_GAMMA), t.grad(RTFS_P_AT_BETA), t.grad(RTFS_P_AT_SLOPE), nframes, Tc, H};
-        const int smem = (64 * 65 + 96 * 65 + 64) * 4;
+        const int smem = (64 * 65 + 96 * 65 + 768 + 16) * 4;
         static SmemCfg cfg;
         CKN(ensure_smem(att_qkv_bwd_kernel, smem, cfg));
-        att_qkv_bwd_kernel<<<frame_grid, 256, smem, t.st>>>(a);
+        att_qkv_bwd_kernel<<<frame_grid, 384, smem, t.st>>>(a);
         CK(cudaGetLastError());
         PlainLoader al{gdpre, 96, 96};
         AddEpi ep{d_in, 64, d_out};  // + the residual path (out = proj + g)
         CK((launch_gemm<64, 96, false>(al, t.P[RTFS_P_AT_WQKVT], ep, M, 64, t.st)));
         PlainLoader xl{g_in, 64, 64}, yl{gdpre, 96, 96};
-        CK((launch_wgrad<true>(xl, yl, t.grad(RTFS_P_AT_WQKV), 64, M, 96, 64, t.st)));
+        CK((launch_wgrad<false>(xl, yl, t.grad(RTFS_P_AT_WQKV), 64, M, 96, 64, t.st)));
         RUN(colsum<96>(t, gdpre, M, t.grad(RTFS_P_AT_BQKV)));
     }
     return 0;
@@ -416,7 +416,7 @@ int run_block_bwd(const TrainCtx& t, const Ctx& c, const float* x, const float* 
         StoreEpi ep{hDE, 64, nullptr};
         CK((launch_gemm<64, 256, false>(al, P[RTFS_P_RC_WT], ep, M, 64, t.st)));
         PlainLoader xl{hE, 64, 64}, yl{dout, 256, 256};
-        CK((launch_wgrad<true>(xl, yl, t.grad(RTFS_P_RC_W), 64, M, 256, 64, t.st)));
+        CK((launch_wgrad<false>(xl, yl, t.grad(RTFS_P_RC_W), 64, M, 256, 64, t.st)));
         RUN(colsum<256>(t, dout, M, t.grad(RTFS_P_RC_B)));
     }
     // B3-B5: concat_layers.0 = TF-AR(f0, f1) + d0                                                tdanet.py:127-129
@@ -507,7 +507,7 @@ int run_block_bwd(const TrainCtx& t, const Ctx& c, const float* x, const float* 
     {
         GateLoader xl{x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], 256};
         PlainLoader yl{hT, 64, 64};
-        CK((launch_wgrad<true>(xl, yl, t.grad(RTFS_P_PJ_W), 256, M, 64, 256, t.st)));
+        CK((launch_wgrad<false>(xl, yl, t.grad(RTFS_P_PJ_W), 256, M, 64, 256, t.st)));
         RUN(colsum<64>(t, hT, M, t.grad(RTFS_P_PJ_B)));
         PlainLoader al{hT, 64, 64};
         GateBwdEpi ep{dx, dout, x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], t.grad(RTFS_P_GW_W), t.grad(RTFS_P_GW_B), t.grad(RTFS_P_GW_A), dacc, dacc_init ? 1 : 0};
@@ -669,7 +669,7 @@ int rtfs_avnet_backward(const float* const* params, float* const* grads, const f
             CK((launch_gemm<128, 256, false>(al, params[RTFS_P_MK_WT], ep, M, 256, t.st)));
             PreluLoader xl{refined, params[RTFS_P_MK_A], 256};
             PlainLoader yl{dM, 256, 256};
-            CK((launch_wgrad<true>(xl, yl, t.grad(RTFS_P_MK_W), 256, M, 256, 256, t.st)));
+            CK((launch_wgrad<false>(xl, yl, t.grad(RTFS_P_MK_W), 256, M, 256, 256, t.st)));
             RUN(colsum<256>(t, dM, M, t.grad(RTFS_P_MK_B)));
         }
         // block passes R-1 .. 1: the gradient w.r.t. a pass's input is the gradient w.r.t. the previous pass's output AND is
@@ -738,7 +738,7 @@ int rtfs_avnet_backward(const float* const* params, float* const* grads, const f
         const GlnRef nA0 = c0.gln(RTFS_ST_A0, RTFS_P_BN_GAMMA, RTFS_P_BN_BETA, d.P * 256);
         GlnActLoader<256, 1> xl{a0, nA0, (int)d.P, d.B};
         PlainLoader yl{dA1, 256, 256};
-        CK((launch_wgrad<true>(xl, yl, t.grad(RTFS_P_BN_W), 256, M, 256, 256, t.st)));
+        CK((launch_wgrad<false>(xl, yl, t.grad(RTFS_P_BN_W), 256, M, 256, 256, t.st)));
         RUN(colsum<256>(t, dA1, M, t.grad(RTFS_P_BN_B)));
         PlainLoader al{dA1, 256, 256};
         StoreEpi ep{dA, 256, nullptr};  // gradient w.r.t. relu(gLN(a0))

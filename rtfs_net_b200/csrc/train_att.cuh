@@ -195,102 +195,104 @@ DEVINL void qkv_group(int j, int& grp, int& col0, int& E, int& goff) {
     else { grp = 8 + ((j - 32) >> 4); col0 = 32 + (grp - 8) * 16; E = 16; goff = 2048 + (grp - 8) * 1024; }
 }
 
-__global__ void __launch_bounds__(256) att_qkv_bwd_kernel(AttQkvBwdArgs a) {
+// 384 threads: thread = (column j of the 96 conv outputs, row phase fb): it owns rows f = fb + 4i, i < 16, of its column, so the
+// LN affine gradients of its 16 (f, j) elements stay in registers over the frame loop and the per-group LN sums are formed from
+// one partial per thread (shared-memory table [4][96], no atomics).
+__global__ void __launch_bounds__(384) att_qkv_bwd_kernel(AttQkvBwdArgs a) {
     extern __shared__ __align__(16) float sm[];
-    float* Xs = sm;              // [64][65]
-    float* Ws = Xs + 64 * 65;    // [96][65]
-    float* st = Ws + 96 * 65;    // [4][12]: sum / centred sumsq / m1 / m2 per group
-    float* dsl_s = st + 48;      // [12]
-    const int tid = threadIdx.x;
-    for (int i = tid; i < 96 * 64; i += 256) Ws[(i >> 6) * 65 + (i & 63)] = __ldg(a.W + i);
+    float* Xs = sm;               // [64][65]
+    float* Ws = Xs + 64 * 65;     // [96][65]
+    float* part = Ws + 96 * 65;   // [2][4][96] per-thread partial sums (two quantities)
+    float* dsl_s = part + 768;    // [12]
+    const int tid = threadIdx.x, j = tid % 96, fb = tid / 96;
+    for (int i = tid; i < 96 * 64; i += 384) Ws[(i >> 6) * 65 + (i & 63)] = __ldg(a.W + i);
     if (tid < 12) dsl_s[tid] = 0.f;
-    // thread's 24 elements e = tid + 256*i: f = e / 96, j = e % 96 (the per-element group data is recomputed where it is
-    // needed: keeping it in registers for 24 elements spills)
-    float dg[24], db[24];
+    int grp, col0, E, goff;
+    qkv_group(j, grp, col0, E, goff);
+    const float bj = __ldg(a.bias + j), sl = __ldg(a.slope + grp);
+    const float invn = 1.f / (float)(64 * E);
+    const int h = grp & 3, e = j - col0;
+    float gmm[16], dg[16], db[16];
 #pragma unroll
-    for (int i = 0; i < 24; ++i) dg[i] = db[i] = 0.f;
+    for (int i = 0; i < 16; ++i) {
+        gmm[i] = __ldg(a.gamma + goff + (fb + 4 * i) * E + e);
+        dg[i] = db[i] = 0.f;
+    }
+    float dsl = 0.f;
+    // sum over the group's E columns x 4 row phases of one partial per thread
+    auto group_sum = [&](const float* tab) {
+        float s = 0.f;
+        for (int q = 0; q < 4; ++q)
+            for (int c = 0; c < E; ++c) s += tab[q * 96 + col0 + c];
+        return s;
+    };
     for (int fr = blockIdx.x; fr < a.nframes; fr += gridDim.x) {
         __syncthreads();
         const float* xin = a.x + (long long)fr * 4096;
-        for (int i = tid; i < 4096; i += 256) Xs[(i >> 6) * 65 + (i & 63)] = __ldg(xin + i);
-        if (tid < 48) st[tid] = 0.f;
+        for (int i = tid; i < 4096; i += 384) Xs[(i >> 6) * 65 + (i & 63)] = __ldg(xin + i);
         __syncthreads();
-        float act[24];   // PReLU(pre), later xhat
-        unsigned neg = 0;  // bit i: pre < 0
-        float prv[24];   // pre (needed for the slope gradient)
+        float pre[16];
 #pragma unroll
-        for (int i = 0; i < 24; ++i) {
-            const int e = tid + 256 * i, f = e / 96, j = e - f * 96;
-            int grp, col0, E, goff;
-            qkv_group(j, grp, col0, E, goff);
-            float p = __ldg(a.bias + j);
-            const float* xr = Xs + f * 65;
-            const float* wr = Ws + j * 65;
-#pragma unroll 8
-            for (int c = 0; c < 64; ++c) p = fmaf(xr[c], wr[c], p);
-            prv[i] = p;
-            if (p < 0.f) neg |= 1u << i;
-            act[i] = prelu(p, __ldg(a.slope + grp));
-            atomicAdd(st + grp, act[i]);
-        }
-        __syncthreads();
+        for (int i = 0; i < 16; ++i) pre[i] = bj;
+        for (int c = 0; c < 64; ++c) {
+            const float w = Ws[j * 65 + c];
 #pragma unroll
-        for (int i = 0; i < 24; ++i) {
-            const int e = tid + 256 * i, f = e / 96, j = e - f * 96;
-            int grp, col0, E, goff;
-            qkv_group(j, grp, col0, E, goff);
-            const float d = act[i] - st[grp] / (float)(64 * E);
-            atomicAdd(st + 12 + grp, d * d);
+            for (int i = 0; i < 16; ++i) pre[i] = fmaf(Xs[(fb + 4 * i) * 65 + c], w, pre[i]);
         }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += prelu(pre[i], sl);
+        part[fb * 96 + j] = s;
         __syncthreads();
+        const float mu = group_sum(part) * invn;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float d = prelu(pre[i], sl) - mu;
+            q += d * d;
+        }
+        part[384 + fb * 96 + j] = q;
+        __syncthreads();
+        const float rs = 1.f / sqrtf(group_sum(part + 384) * invn + RTFS_EPS);
         const int b = fr / a.Tc, t = fr - b * a.Tc;
-        float gy[24];
+        const long long tok = ((long long)b * a.H + h) * a.Tc + t;
+        const float* src = grp < 4 ? a.dq + tok * 256 : (grp < 8 ? a.dk + tok * 256 : a.dv + tok * 1024);
+        float dy[16], s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 24; ++i) {
-            const int e = tid + 256 * i, f = e / 96, j = e - f * 96;
-            int grp, col0, E, goff;
-            qkv_group(j, grp, col0, E, goff);
-            const float invn = 1.f / (float)(64 * E);
-            const float mu = st[grp] * invn;
-            const float rs = 1.f / sqrtf(st[12 + grp] * invn + RTFS_EPS);
-            act[i] = (act[i] - mu) * rs;  // xhat
-            const int h = grp & 3, inner = f * E + (j - col0);
-            const long long tok = ((long long)b * a.H + h) * a.Tc + t;
-            const float* src = grp < 4 ? a.dq + tok * 256 : (grp < 8 ? a.dk + tok * 256 : a.dv + tok * 1024);
-            const float dy = __ldg(src + inner);
-            dg[i] += dy * act[i];
-            db[i] += dy;
-            gy[i] = dy * __ldg(a.gamma + goff + inner);
-            atomicAdd(st + 24 + grp, gy[i]);
-            atomicAdd(st + 36 + grp, gy[i] * act[i]);
+        for (int i = 0; i < 16; ++i) {
+            dy[i] = __ldg(src + (fb + 4 * i) * E + e);
+            const float xh = (prelu(pre[i], sl) - mu) * rs;
+            dg[i] += dy[i] * xh;
+            db[i] += dy[i];
+            const float gy = dy[i] * gmm[i];
+            s1 += gy;
+            s2 += gy * xh;
         }
+        __syncthreads();  // every thread has read the centred-square table
+        part[fb * 96 + j] = s1;
+        part[384 + fb * 96 + j] = s2;
         __syncthreads();
+        const float m1 = group_sum(part) * invn, m2 = group_sum(part + 384) * invn;
         float* dp = a.dpre + (long long)fr * (64 * 96);
 #pragma unroll
-        for (int i = 0; i < 24; ++i) {
-            const int e = tid + 256 * i, f = e / 96, j = e - f * 96;
-            int grp, col0, E, goff;
-            qkv_group(j, grp, col0, E, goff);
-            const float invn = 1.f / (float)(64 * E);
-            const float rs = 1.f / sqrtf(st[12 + grp] * invn + RTFS_EPS);
-            float da = (gy[i] - st[24 + grp] * invn - act[i] * st[36 + grp] * invn) * rs;
-            if ((neg >> i) & 1u) {
-                atomicAdd(dsl_s + grp, da * prv[i]);
-                da *= __ldg(a.slope + grp);
+        for (int i = 0; i < 16; ++i) {
+            const float xh = (prelu(pre[i], sl) - mu) * rs;
+            float da = (dy[i] * gmm[i] - m1 - xh * m2) * rs;
+            if (pre[i] < 0.f) {
+                dsl += da * pre[i];
+                da *= sl;
             }
-            dp[e] = da;
+            dp[(fb + 4 * i) * 96 + j] = da;
         }
     }
-    __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 24; ++i) {
-        const int e = tid + 256 * i, f = e / 96, j = e - f * 96;
-        int grp, col0, E, goff;
-        qkv_group(j, grp, col0, E, goff);
-        const int gi = goff + f * E + (j - col0);
+    for (int i = 0; i < 16; ++i) {
+        const int gi = goff + (fb + 4 * i) * E + e;
         atomicAdd(a.dgamma + gi, dg[i]);
         atomicAdd(a.dbeta + gi, db[i]);
     }
+    atomicAdd(dsl_s + grp, dsl);
+    __syncthreads();
     if (tid < 12 && dsl_s[tid] != 0.f) atomicAdd(a.dslope + tid, dsl_s[tid]);
 }
 

@@ -8,6 +8,8 @@
 //     the overlapping unfold views of the dual-path RNN) is re-formed on load instead of being stored in the forward;
 //   * bgemm_kernel: batched small fp32 GEMM with arbitrary strides (attention score / context gradients per (b, head)).
 #pragma once
+#include <cstdlib>
+
 #include "gemm.cuh"
 
 namespace rtfs {
@@ -15,27 +17,46 @@ namespace rtfs {
 // ------------------------------------------------------------------------------------------------------------ wgrad
 constexpr int WG_LD = 72;  // 64 + 8: fragment reads of 8 consecutive columns x 4 rows hit 32 distinct banks
 
-// PREC3: error-compensated 3xTF32 (hi/lo split of both operands) -- the reduction runs over up to 10^6 rows and the
-// result is compared against fp32 autograd of the reference, so the default path keeps fp32-level products.
-template <bool PREC3, class XL, class YL>
+// CTA tile: 64 (n) x 64*KT (k) outputs, rows streamed in 32-row sub-chunks of 128-row groups (the loaders' tile contract).
+//   KT = 1: 8 warps = 4 (n, 16 rows) x 2 (k, 32 columns)           -- the K = 64 shapes
+//   KT = 4: 8 warps = 2 (n, 32 rows) x 4 (k, 64 columns)           -- K >= 256: dY is re-read K/256 instead of K/64 times
+// Operands are rounded to TF32 when they are staged (one rounding per element, none in the MMA loop).  The products of a
+// reduction over 10^4..10^6 rows are individually rounded to nearest, so their errors average out: plain TF32 is far below the
+// TF32 noise the forward activations already carry.  PREC3 (3xTF32: hi/lo planes of both operands staged separately) is kept
+// for the tiny-K encoder / decoder filters that touch the waveform directly, and as an A/B switch (RTFS_WGRAD_3X=1).
+template <bool PREC3, int KT, class XL, class YL>
 __global__ void __launch_bounds__(256) wgrad_kernel(XL xl, YL yl, float* __restrict__ dW, int ldw, int M, int N, int K, int groups_per_cta) {
+    constexpr int LDX = 64 * KT + 8;
+    constexpr int NP = PREC3 ? 2 : 1;           // operand planes: hi (, lo)
+    constexpr int WM = KT == 1 ? 1 : 2;         // 16-row n tiles per warp
+    constexpr int WN = KT == 1 ? 4 : 8;         // 8-column k tiles per warp
     extern __shared__ __align__(16) float smem[];
-    float* Ys = smem;                 // [32][WG_LD]
-    float* Xs = smem + 32 * WG_LD;    // [32][WG_LD]
-    float* extra_x = Xs + 32 * WG_LD;
+    float* Ys = smem;                            // [NP][32][WG_LD]
+    float* Xs = Ys + NP * 32 * WG_LD;            // [NP][32][LDX]
+    float* extra_x = Xs + NP * 32 * LDX;
     float* extra_y = extra_x + XL::kExtra;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int ntn = (N + 63) / 64;
-    const int n0 = (blockIdx.x % ntn) * 64, k0 = (blockIdx.x / ntn) * 64;
-    const int mt = warp & 3, nt0 = (warp >> 2) * 4;  // warp: n rows mt*16..+16, k columns nt0*8..+32
-    float acc[4][4];
+    const int n0 = (blockIdx.x % ntn) * 64, k0 = (blockIdx.x / ntn) * (64 * KT);
+    const int wn0 = KT == 1 ? (warp & 3) * 16 : (warp & 1) * 32;   // first n row of the warp
+    const int wk0 = KT == 1 ? (warp >> 2) * 32 : (warp >> 1) * 64; // first k column of the warp
+    float acc[WM][WN][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    for (int a = 0; a < WM; ++a)
+#pragma unroll
+        for (int b = 0; b < WN; ++b) acc[a][b][0] = acc[a][b][1] = acc[a][b][2] = acc[a][b][3] = 0.f;
 
     const int ngroups = (M + 127) / 128;
     const int g_begin = blockIdx.y * groups_per_cta;
     const int g_end = min(ngroups, g_begin + groups_per_cta);
     const int r_ld = tid >> 3, c_ld = (tid & 7) * 4;
+    auto stage = [&](float* dst, int ld, int col, float4 v) {
+        const float4 h = make_float4(tf32r(v.x), tf32r(v.y), tf32r(v.z), tf32r(v.w));
+        *reinterpret_cast<float4*>(dst + r_ld * ld + col) = h;
+        if (PREC3)
+            *reinterpret_cast<float4*>(dst + 32 * ld + r_ld * ld + col) =
+                make_float4(tf32r(v.x - h.x), tf32r(v.y - h.y), tf32r(v.z - h.z), tf32r(v.w - h.w));
+    };
     for (int grp = g_begin; grp < g_end; ++grp) {
         __syncthreads();  // previous group's tables / tiles are no longer read
         xl.init(grp * 128, M, extra_x);
@@ -44,76 +65,112 @@ __global__ void __launch_bounds__(256) wgrad_kernel(XL xl, YL yl, float* __restr
 #pragma unroll 1
         for (int i = 0; i < 4; ++i) {
             if (grp * 128 + 32 * i >= M) break;
-            // 32 rows x 64 columns of each operand: thread -> row r_ld, columns c_ld and c_ld + 32
-            const float4 x0 = (k0 + c_ld < K) ? xl.load(i, k0 + c_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 x1 = (k0 + c_ld + 32 < K) ? xl.load(i, k0 + c_ld + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 y0 = (n0 + c_ld < N) ? yl.load(i, n0 + c_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 y1 = (n0 + c_ld + 32 < N) ? yl.load(i, n0 + c_ld + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+            // 32 rows x (64*KT | 64) columns: thread -> row r_ld, columns c_ld + 32*j
+            float4 xv[2 * KT], yv[2];
+#pragma unroll
+            for (int j = 0; j < 2 * KT; ++j)
+                xv[j] = (k0 + c_ld + 32 * j < K) ? xl.load(i, k0 + c_ld + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                yv[j] = (n0 + c_ld + 32 * j < N) ? yl.load(i, n0 + c_ld + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
             __syncthreads();  // the previous sub-chunk's MMAs are done
-            *reinterpret_cast<float4*>(Xs + r_ld * WG_LD + c_ld) = x0;
-            *reinterpret_cast<float4*>(Xs + r_ld * WG_LD + c_ld + 32) = x1;
-            *reinterpret_cast<float4*>(Ys + r_ld * WG_LD + c_ld) = y0;
-            *reinterpret_cast<float4*>(Ys + r_ld * WG_LD + c_ld + 32) = y1;
+#pragma unroll
+            for (int j = 0; j < 2 * KT; ++j) stage(Xs, LDX, c_ld + 32 * j, xv[j]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) stage(Ys, WG_LD, c_ld + 32 * j, yv[j]);
             __syncthreads();
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
                 // A (16 n x 8 rows): A[n][r] = Ys[r][n] ; B (8 rows x 8 k): B[r][k] = Xs[r][k]
-                const float* ya = Ys + (ks * 8 + t) * WG_LD + mt * 16 + g;
-                const float a0 = ya[0], a1 = ya[8], a2 = ya[4 * WG_LD], a3 = ya[4 * WG_LD + 8];
-                uint32_t ah[4] = {f2tf32(a0), f2tf32(a1), f2tf32(a2), f2tf32(a3)}, al[4];
-                if (PREC3) {
-                    al[0] = f2tf32(a0 - __uint_as_float(ah[0]));
-                    al[1] = f2tf32(a1 - __uint_as_float(ah[1]));
-                    al[2] = f2tf32(a2 - __uint_as_float(ah[2]));
-                    al[3] = f2tf32(a3 - __uint_as_float(ah[3]));
+                uint32_t ah[WM][4], al[WM][4];
+#pragma unroll
+                for (int a = 0; a < WM; ++a) {
+                    const float* ya = Ys + (ks * 8 + t) * WG_LD + wn0 + a * 16 + g;
+                    ah[a][0] = __float_as_uint(ya[0]);
+                    ah[a][1] = __float_as_uint(ya[8]);
+                    ah[a][2] = __float_as_uint(ya[4 * WG_LD]);
+                    ah[a][3] = __float_as_uint(ya[4 * WG_LD + 8]);
+                    if (PREC3) {
+                        const float* yl2 = ya + 32 * WG_LD;
+                        al[a][0] = __float_as_uint(yl2[0]);
+                        al[a][1] = __float_as_uint(yl2[8]);
+                        al[a][2] = __float_as_uint(yl2[4 * WG_LD]);
+                        al[a][3] = __float_as_uint(yl2[4 * WG_LD + 8]);
+                    }
                 }
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) {
-                    const float* xb = Xs + (ks * 8 + t) * WG_LD + (nt0 + ni) * 8 + g;
-                    const float b0 = xb[0], b1 = xb[4 * WG_LD];
-                    uint32_t bh[2] = {f2tf32(b0), f2tf32(b1)};
+                for (int b = 0; b < WN; ++b) {
+                    const float* xb = Xs + (ks * 8 + t) * LDX + wk0 + b * 8 + g;
+                    uint32_t bh[2] = {__float_as_uint(xb[0]), __float_as_uint(xb[4 * LDX])};
+                    uint32_t bl[2] = {0u, 0u};
                     if (PREC3) {
-                        uint32_t bl[2] = {f2tf32(b0 - __uint_as_float(bh[0])), f2tf32(b1 - __uint_as_float(bh[1]))};
-                        mma_tf32(acc[ni], al, bh);
-                        mma_tf32(acc[ni], ah, bl);
+                        bl[0] = __float_as_uint(xb[32 * LDX]);
+                        bl[1] = __float_as_uint(xb[32 * LDX + 4 * LDX]);
                     }
-                    mma_tf32(acc[ni], ah, bh);
+#pragma unroll
+                    for (int a = 0; a < WM; ++a) {
+                        if (PREC3) {
+                            mma_tf32(acc[a][b], al[a], bh);
+                            mma_tf32(acc[a][b], ah[a], bl);
+                        }
+                        mma_tf32(acc[a][b], ah[a], bh);
+                    }
                 }
             }
         }
     }
     // d0=(g,2t) d1=(g,2t+1) d2=(g+8,2t) d3=(g+8,2t+1): row = n, column = k
 #pragma unroll
-    for (int ni = 0; ni < 4; ++ni) {
-        const int n = n0 + mt * 16 + g, k = k0 + (nt0 + ni) * 8 + 2 * t;
-        if (k < K) {
-            if (n < N) atomicAdd(dW + (long long)n * ldw + k, acc[ni][0]);
-            if (n + 8 < N) atomicAdd(dW + (long long)(n + 8) * ldw + k, acc[ni][2]);
+    for (int a = 0; a < WM; ++a)
+#pragma unroll
+        for (int b = 0; b < WN; ++b) {
+            const int n = n0 + wn0 + a * 16 + g, k = k0 + wk0 + b * 8 + 2 * t;
+            if (k < K) {
+                if (n < N) atomicAdd(dW + (long long)n * ldw + k, acc[a][b][0]);
+                if (n + 8 < N) atomicAdd(dW + (long long)(n + 8) * ldw + k, acc[a][b][2]);
+            }
+            if (k + 1 < K) {
+                if (n < N) atomicAdd(dW + (long long)n * ldw + k + 1, acc[a][b][1]);
+                if (n + 8 < N) atomicAdd(dW + (long long)(n + 8) * ldw + k + 1, acc[a][b][3]);
+            }
         }
-        if (k + 1 < K) {
-            if (n < N) atomicAdd(dW + (long long)n * ldw + k + 1, acc[ni][1]);
-            if (n + 8 < N) atomicAdd(dW + (long long)(n + 8) * ldw + k + 1, acc[ni][3]);
-        }
-    }
 }
 
-// dW[N][K] (row stride ldw) += sum_{row < M} Y[row][n] * X[row][k]
-template <bool PREC3, class XL, class YL>
-inline cudaError_t launch_wgrad(const XL& xl, const YL& yl, float* dW, int ldw, int M, int N, int K, cudaStream_t st) {
-    auto kern = wgrad_kernel<PREC3, XL, YL>;
-    const int smem = (2 * 32 * WG_LD + XL::kExtra + YL::kExtra) * 4;
+template <bool PREC3, int KT, class XL, class YL>
+inline cudaError_t launch_wgrad_t(const XL& xl, const YL& yl, float* dW, int ldw, int M, int N, int K, cudaStream_t st) {
+    auto kern = wgrad_kernel<PREC3, KT, XL, YL>;
+    const int smem = ((PREC3 ? 2 : 1) * 32 * (WG_LD + 64 * KT + 8) + XL::kExtra + YL::kExtra) * 4;
     static SmemCfg cfg;
     if (smem > 48 * 1024)
         if (cudaError_t e = ensure_smem(kern, smem, cfg); e != cudaSuccess) return e;
-    const int tiles = ((N + 63) / 64) * ((K + 63) / 64);
+    const int tiles = ((N + 63) / 64) * ((K + 64 * KT - 1) / (64 * KT));
     const int ngroups = (M + 127) / 128;
-    int splits = (sm_count() * 6 + tiles - 1) / tiles;  // ~6 CTAs per SM in total
+    int splits = (sm_count() * 4 + tiles - 1) / tiles;  // ~4 CTAs per SM in total
     if (splits > ngroups) splits = ngroups;
     if (splits < 1) splits = 1;
     const int gpc = (ngroups + splits - 1) / splits;
     splits = (ngroups + gpc - 1) / gpc;
     kern<<<dim3(tiles, splits), 256, smem, st>>>(xl, yl, dW, ldw, M, N, K, gpc);
     return cudaGetLastError();
+}
+
+inline bool wgrad_3x() {  // RTFS_WGRAD_3X=1: error-compensated 3xTF32 in every weight-gradient reduction (A/B of the TF32 default)
+    static const bool v = [] {
+        const char* e = getenv("RTFS_WGRAD_3X");
+        return e != nullptr && e[0] != '\0' && e[0] != '0';
+    }();
+    return v;
+}
+
+// dW[N][K] (row stride ldw) += sum_{row < M} Y[row][n] * X[row][k].  EXACT: 3xTF32 regardless of the switch.
+template <bool EXACT, class XL, class YL>
+inline cudaError_t launch_wgrad(const XL& xl, const YL& yl, float* dW, int ldw, int M, int N, int K, cudaStream_t st) {
+    if (EXACT || wgrad_3x()) {
+        if (K >= 256) return launch_wgrad_t<true, 4>(xl, yl, dW, ldw, M, N, K, st);
+        return launch_wgrad_t<true, 1>(xl, yl, dW, ldw, M, N, K, st);
+    }
+    if (K >= 256) return launch_wgrad_t<false, 4>(xl, yl, dW, ldw, M, N, K, st);
+    return launch_wgrad_t<false, 1>(xl, yl, dW, ldw, M, N, K, st);
 }
 
 // ------------------------------------------------------------------------------------------- epilogues of launch_gemm

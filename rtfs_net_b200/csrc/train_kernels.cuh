@@ -195,31 +195,38 @@ struct DwBwdDataArgs {
 
 template <int NW>
 __global__ void __launch_bounds__(256) dw_bwd_data_kernel(DwBwdDataArgs<NW> a) {
+    const int row_off = a.Fo * 64;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < a.total4; idx += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(idx & 15) * 4;
-        const long long pos = idx >> 4;
-        const int f = (int)(pos % a.Fi);
-        const long long bt = pos / a.Fi;
-        const int t = (int)(bt % a.Ti);
-        const long long b = bt / a.Ti;
+        const int pos = (int)(idx >> 4);
+        const int f = pos % a.Fi;
+        const int bt = pos / a.Fi;
+        const int t = bt % a.Ti;
+        const int b = bt / a.Ti;
+        // output rows / columns that read input (t, f) through tap i / j: to = (t + 1 - i) / s when divisible and in range
+        int to[4], fo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int v = t + 1 - i, w = f + 1 - i;
+            if (a.stride == 2) {
+                to[i] = (v & 1) ? -1 : (v >> 1);
+                fo[i] = (w & 1) ? -1 : (w >> 1);
+            } else {
+                to[i] = v;
+                fo[i] = w;
+            }
+            if ((unsigned)to[i] >= (unsigned)a.To) to[i] = -1;
+            if ((unsigned)fo[i] >= (unsigned)a.Fo) fo[i] = -1;
+        }
+        const long long bbase = (long long)b * a.To * a.Fo * 64 + c;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            int to = t + 1 - i;
-            if (a.stride == 2) {
-                if (to & 1) continue;
-                to >>= 1;
-            }
-            if (to < 0 || to >= a.To) continue;
+            if (to[i] < 0) continue;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                int fo = f + 1 - j;
-                if (a.stride == 2) {
-                    if (fo & 1) continue;
-                    fo >>= 1;
-                }
-                if (fo < 0 || fo >= a.Fo) continue;
-                const long long o = (((b * a.To + to) * a.Fo) + fo) * 64 + c;
+                if (fo[j] < 0) continue;
+                const long long o = bbase + to[i] * row_off + fo[j] * 64;
 #pragma unroll
                 for (int k = 0; k < NW; ++k) {
                     const float4 d = ldg4(a.dy[k] + o), w = ldg4(a.w[k] + (i * 4 + j) * 64 + c);
@@ -256,49 +263,70 @@ __global__ void __launch_bounds__(256) dw_bwd_weight_kernel(DwBwdWArgs a) {
     for (int i = threadIdx.x; i < 17 * 64; i += blockDim.x) sh[i] = 0.f;
     __syncthreads();
     const int c = (threadIdx.x & 15) * 4;
-    const long long npos = (long long)a.B * a.To * a.Fo;
+    const int npos = a.B * a.To * a.Fo;  // < 2^31 / 64 by the library's size limit
+    const int row_off = a.Fi * 64;       // element offset between input rows
     float4 acc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 ab = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long pos = (long long)blockIdx.x * 16 + (threadIdx.x >> 4); pos < npos; pos += (long long)gridDim.x * 16) {
-        const int fo = (int)(pos % a.Fo);
-        const long long bt = pos / a.Fo;
-        const int to = (int)(bt % a.To);
-        const long long b = bt / a.To;
-        const float4 d = ldg4(a.dy + pos * 64 + c);
+    for (int pos = blockIdx.x * 16 + (threadIdx.x >> 4); pos < npos; pos += gridDim.x * 16) {
+        const int fo = pos % a.Fo;
+        const int bt = pos / a.Fo;
+        const int to = bt % a.To;
+        const int b = bt / a.To;
+        const float4 d = ldg4(a.dy + (long long)pos * 64 + c);
         ab.x += d.x;
         ab.y += d.y;
         ab.z += d.z;
         ab.w += d.w;
         const int t0 = to * a.stride - 1, f0 = fo * a.stride - 1;
+        // one 64-bit base per position, 32-bit tap offsets, 4 + 4 validity flags
+        const float* base = a.x + (((long long)b * a.Ti + t0) * a.Fi + f0) * 64 + c;
+        bool vt[4], vf[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int t = t0 + i;
-            if (t < 0 || t >= a.Ti) continue;
+            vt[i] = (unsigned)(t0 + i) < (unsigned)a.Ti;
+            vf[i] = (unsigned)(f0 + i) < (unsigned)a.Fi;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int f = f0 + j;
-                if (f < 0 || f >= a.Fi) continue;
-                const float4 x = ldg4(a.x + (((b * a.Ti + t) * a.Fi) + f) * 64 + c);
-                acc[i * 4 + j].x = fmaf(d.x, x.x, acc[i * 4 + j].x);
-                acc[i * 4 + j].y = fmaf(d.y, x.y, acc[i * 4 + j].y);
-                acc[i * 4 + j].z = fmaf(d.z, x.z, acc[i * 4 + j].z);
-                acc[i * 4 + j].w = fmaf(d.w, x.w, acc[i * 4 + j].w);
+                if (vt[i] && vf[j]) {
+                    const float4 x = ldg4(base + i * row_off + j * 64);
+                    acc[i * 4 + j].x = fmaf(d.x, x.x, acc[i * 4 + j].x);
+                    acc[i * 4 + j].y = fmaf(d.y, x.y, acc[i * 4 + j].y);
+                    acc[i * 4 + j].z = fmaf(d.z, x.z, acc[i * 4 + j].z);
+                    acc[i * 4 + j].w = fmaf(d.w, x.w, acc[i * 4 + j].w);
+                }
             }
         }
     }
+    // lanes l and l + 16 of a warp hold the same channel quad: fold them before the shared-memory atomics
+    const bool lead = (threadIdx.x & 16) == 0;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        atomicAdd(sh + k * 64 + c, acc[k].x);
-        atomicAdd(sh + k * 64 + c + 1, acc[k].y);
-        atomicAdd(sh + k * 64 + c + 2, acc[k].z);
-        atomicAdd(sh + k * 64 + c + 3, acc[k].w);
+        acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, 16);
+        acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, 16);
+        acc[k].z += __shfl_xor_sync(0xffffffffu, acc[k].z, 16);
+        acc[k].w += __shfl_xor_sync(0xffffffffu, acc[k].w, 16);
+        if (lead) {
+            atomicAdd(sh + k * 64 + c, acc[k].x);
+            atomicAdd(sh + k * 64 + c + 1, acc[k].y);
+            atomicAdd(sh + k * 64 + c + 2, acc[k].z);
+            atomicAdd(sh + k * 64 + c + 3, acc[k].w);
+        }
     }
-    atomicAdd(sh + 16 * 64 + c, ab.x);
-    atomicAdd(sh + 16 * 64 + c + 1, ab.y);
-    atomicAdd(sh + 16 * 64 + c + 2, ab.z);
-    atomicAdd(sh + 16 * 64 + c + 3, ab.w);
+    ab.x += __shfl_xor_sync(0xffffffffu, ab.x, 16);
+    ab.y += __shfl_xor_sync(0xffffffffu, ab.y, 16);
+    ab.z += __shfl_xor_sync(0xffffffffu, ab.z, 16);
+    ab.w += __shfl_xor_sync(0xffffffffu, ab.w, 16);
+    if (lead) {
+        atomicAdd(sh + 16 * 64 + c, ab.x);
+        atomicAdd(sh + 16 * 64 + c + 1, ab.y);
+        atomicAdd(sh + 16 * 64 + c + 2, ab.z);
+        atomicAdd(sh + 16 * 64 + c + 3, ab.w);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < 16 * 64; i += blockDim.x) atomicAdd(a.dw + i, sh[i]);
     if (a.dbias != nullptr)
@@ -427,21 +455,46 @@ __global__ void __launch_bounds__(256) tfar_bwd_global_kernel(TfarArgs a, const 
 __global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__ dg0, float* dd0, int T, int F, int Tc, int Fc, long long total4) {
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total4; idx += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(idx & 15) * 4;
-        const long long pos = idx >> 4;
-        const int f = (int)(pos % F);
-        const long long bt = pos / F;
-        const int t = (int)(bt % T);
-        const long long b = bt / T;
-        const int ic = (int)(((long long)t * Tc) / T), jc = (int)(((long long)f * Fc) / F);
+        const int pos = (int)(idx >> 4);
+        const int f = pos % F;
+        const int bt = pos / F;
+        const int t = bt % T;
+        const int b = bt / T;
+        // windows that contain t: i in {ic - 1, ic, ic + 1} with ic = floor(t * Tc / T); 32-bit arithmetic (T, F < 65536)
+        const int ic = (int)(((unsigned)t * (unsigned)Tc) / (unsigned)T), jc = (int)(((unsigned)f * (unsigned)Fc) / (unsigned)F);
+        int iw[3], jw[3];
+        float wt[3], wf[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int i = ic - 1 + k, j = jc - 1 + k;
+            iw[k] = -1;
+            jw[k] = -1;
+            wt[k] = wf[k] = 0.f;
+            if (i >= 0 && i < Tc) {
+                const int ts = (int)(((unsigned)i * (unsigned)T) / (unsigned)Tc), te = (int)(((unsigned)(i + 1) * (unsigned)T + Tc - 1) / (unsigned)Tc);
+                if (t >= ts && t < te) {
+                    iw[k] = i;
+                    wt[k] = 1.f / (float)(te - ts);
+                }
+            }
+            if (j >= 0 && j < Fc) {
+                const int fs = (int)(((unsigned)j * (unsigned)F) / (unsigned)Fc), fe = (int)(((unsigned)(j + 1) * (unsigned)F + Fc - 1) / (unsigned)Fc);
+                if (f >= fs && f < fe) {
+                    jw[k] = j;
+                    wf[k] = 1.f / (float)(fe - fs);
+                }
+            }
+        }
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = max(0, ic - 1); i <= min(Tc - 1, ic + 1); ++i) {
-            const int ts = (int)(((long long)i * T) / Tc), te = ceil_div_i((i + 1) * T, Tc);
-            if (t < ts || t >= te) continue;
-            for (int j = max(0, jc - 1); j <= min(Fc - 1, jc + 1); ++j) {
-                const int fs = (int)(((long long)j * F) / Fc), fe = ceil_div_i((j + 1) * F, Fc);
-                if (f < fs || f >= fe) continue;
-                const float w = 1.f / (float)((te - ts) * (fe - fs));
-                const float4 d = ldg4(dg0 + (((b * Tc + i) * Fc) + j) * 64 + c);
+        const float* base = dg0 + (long long)b * Tc * Fc * 64 + c;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (iw[a] < 0) continue;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (jw[k] < 0) continue;
+                const float w = wt[a] * wf[k];
+                const float4 d = ldg4(base + (iw[a] * Fc + jw[k]) * 64);
                 acc.x = fmaf(d.x, w, acc.x);
                 acc.y = fmaf(d.y, w, acc.y);
                 acc.z = fmaf(d.z, w, acc.z);

@@ -39,6 +39,12 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _event():
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
 def _ptr(t):
     return None if t is None else t.data_ptr()
 
@@ -280,6 +286,35 @@ def pit_snr_loss(est, target):
 
 
 # ------------------------------------------------------------------------------------------------------------ trainer
+class FlatParams:
+    """Parameters and gradients of a module as views of two flat fp32 buffers (device-agnostic: the CPU gloo tests cover the
+    data-parallel exchange).  Every parameter starts on a 256-byte boundary: the kernels read parameters with 16-byte vector
+    loads; the padding stays zero (zero gradient, zero moments, decay of zero)."""
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        self.offsets, n = [], 0
+        for p in self.params:
+            self.offsets.append(n)
+            n += (p.numel() + 63) // 64 * 64
+        self.flat_p = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                k = p.numel()
+                self.flat_p[o:o + k].copy_(p.reshape(-1))
+                p.data = self.flat_p[o:o + k].view(p.shape)
+                p.grad = self.flat_g[o:o + k].view(p.shape)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def exchange(self):
+        """One sum all-reduce of the flat gradient (NCCL over NVLink on the GPU box, gloo in the CPU tests); the 1/world factor
+        is folded into the optimizer kernel."""
+        if self.world > 1:
+            dist.all_reduce(self.flat_g)
+
+
 class Trainer:
     """Native training step: forward + SNR loss + backward + gradient all-reduce + clip + AdamW.
 
@@ -290,44 +325,37 @@ class Trainer:
     def __init__(self, model, lr=1e-3, weight_decay=0.1, betas=(0.9, 0.999), eps=1e-8, clip=5.0):
         self.model = model
         self.lr, self.wd, self.betas, self.eps, self.clip = lr, weight_decay, betas, eps, clip
-        params = [p for p in model.parameters() if p.requires_grad]
-        dev = params[0].device
-        # every parameter starts on a 256-byte boundary of the flat buffer: the kernels read parameters with 16-byte vector
-        # loads; the padding stays zero (zero gradient, zero moments, decay of zero)
-        offs, n = [], 0
-        for p in params:
-            offs.append(n)
-            n += (p.numel() + 63) // 64 * 64
-        self.flat_p = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
-        with torch.no_grad():
-            for p, o in zip(params, offs):
-                k = p.numel()
-                self.flat_p[o:o + k].copy_(p.reshape(-1))
-                p.data = self.flat_p[o:o + k].view(p.shape)
-                p.grad = self.flat_g[o:o + k].view(p.shape)
-        self.params = params
+        self.flat = FlatParams(model)
+        self.flat_p, self.flat_g, self.params, self.world = self.flat.flat_p, self.flat.flat_g, self.flat.params, self.flat.world
+        dev = self.flat_p.device
         self.m = torch.zeros_like(self.flat_p)
         self.v = torch.zeros_like(self.flat_p)
         self.gnorm = torch.zeros(1, device=dev, dtype=torch.float64)
         self.t = 0
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
-    def step(self, wav, target, mouth):
-        """One optimisation step on this rank's batch shard; returns the (local) loss as a 0-d tensor."""
+    def exchange(self):
+        self.flat.exchange()
+
+    def step(self, wav, target, mouth, events=None):
+        """One optimisation step on this rank's batch shard; returns the (local) loss as a 0-d tensor.
+        events: optional list that receives 4 recorded CUDA events (start, after forward+loss, after backward, end)."""
         model = self.model
         model.train()
+        mark = (lambda: events.append(_event())) if events is not None else (lambda: None)
+        mark()
         self.flat_g.zero_()
         est = model(wav, mouth)
         loss, d_est = snr_loss(est.detach(), target, True)
+        mark()
         est.backward(d_est.view_as(est))
-        if self.world > 1:
-            dist.all_reduce(self.flat_g)
+        mark()
+        self.exchange()
         self.t += 1
         with torch.cuda.device(self.flat_p.device):
             _lib.check(_lib.lib().rtfs_adamw_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.flat_p.numel(),
                                                   self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.t, self.clip, 1.0 / self.world,
                                                   self.gnorm.data_ptr(), _stream()), "rtfs_adamw_step")
+        mark()
         return loss
 
 

@@ -64,3 +64,50 @@ def test_two_rank_gloo_sharded_batch():
     assert ret["err"] == 0.0
     assert ret["t_max"] == 2.0
     assert ret["n_sum"] == n_items
+
+
+def _train_worker(rank, world, port, ret):
+    """Data-parallel training plumbing on CPU: flat parameter / gradient buffers, ONE all-reduce of the flat gradient, the
+    SyncBatchNorm statistics pack (sums + count) of the CAF cell."""
+    import sys
+
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    from rtfs_net_b200 import shard
+    from rtfs_net_b200.train import FlatParams
+
+    shard.init("gloo")
+    torch.manual_seed(0)  # same initial weights on every rank, as DDP broadcasts them
+    net = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.PReLU(), torch.nn.Linear(3, 1))
+    flat = FlatParams(net)
+    assert flat.world == world
+    assert all(o % 64 == 0 for o in flat.offsets)
+    assert all(p.data_ptr() == flat.flat_p.data_ptr() + 4 * o for p, o in zip(flat.params, flat.offsets))
+    x = torch.full((4, 5), float(rank + 1))
+    net(x).sum().backward()  # accumulates into the views of flat_g
+    local = flat.flat_g.clone()
+    flat.exchange()
+    bufs = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(bufs, local)
+    ok = torch.allclose(flat.flat_g, sum(bufs))
+    # statistics pack of the CAF BatchNorm under sync_batchnorm (train.py:145): channel sums + element count
+    sums = torch.arange(6, dtype=torch.float64).view(3, 2) * (rank + 1)
+    pack = torch.cat([sums.reshape(-1), torch.tensor([10.0 * (rank + 1)], dtype=torch.float64)])
+    dist.all_reduce(pack)
+    if rank == 0:
+        ret["grad_ok"] = bool(ok)
+        ret["pad_zero"] = float(flat.flat_g[flat.params[0].numel():64].abs().max()) == 0.0
+        ret["pack"] = pack.tolist()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_training_exchange():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_train_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert ret["grad_ok"] and ret["pad_zero"]
+    assert ret["pack"] == [0.0, 3.0, 6.0, 9.0, 12.0, 15.0, 30.0]
