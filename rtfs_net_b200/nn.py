@@ -55,27 +55,17 @@ gLN = GlobalLayerNorm
 
 
 def _norm_cls(name):
-    """normalizations.get: own names first, else torch.nn; None -> Identity (normalizations.py:44-58)."""
-    if name is None:
-        return nn.Identity
-    if callable(name):
-        return name
-    cls = globals().get(name) if name in ("gLN", "GlobalLayerNorm", "LayerNormalization4D") else getattr(nn, name, None)
-    if cls is None:
-        raise ValueError("Could not interpret normalization identifier: " + str(name))
-    return cls
+    """normalizations.get (layers/normalizations.py:44-58)."""
+    from .generic import normalizations_get
+
+    return normalizations_get(name)
 
 
 def _act_cls(name):
-    """activations.get (activations.py:4-18)."""
-    if name is None:
-        return nn.Identity
-    if callable(name):
-        return name
-    cls = getattr(nn, name, None)
-    if cls is None:
-        raise ValueError("Could not interpret activation identifier: " + str(name))
-    return cls
+    """activations.get (layers/activations.py:4-18)."""
+    from .generic import activations_get
+
+    return activations_get(name)
 
 
 class DropPath(nn.Module):
@@ -306,9 +296,6 @@ class InjectionMultiSum(nn.Module):
         return local_emb * gate + g_emb
 
 
-_LAYER_TYPES = {"DualPathRNN": DualPathRNN, "MultiHeadSelfAttention2D": MultiHeadSelfAttention2D, "GlobalAttention": GlobalAttention}
-
-
 class TDANetBlock(nn.Module):
     """RTFS block / VP block (separators/tdanet.py:8-133)."""
 
@@ -320,12 +307,9 @@ class TDANetBlock(nn.Module):
         self.downsample_layers = nn.ModuleList(
             [ConvNormAct(hid_chan, hid_chan, kernel_size, stride=1 if i == 0 else stride, groups=hid_chan, norm_type=norm_type, is2d=is2d)
              for i in range(upsampling_depth)])
-        mods = []
-        for _, layer in layers.items():
-            cls = _LAYER_TYPES.get(layer["layer_type"])
-            if cls is None:
-                raise NotImplementedError(f"layer type {layer['layer_type']} is outside the RTFS-Net hot path")
-            mods.append(cls(in_chan=hid_chan, **layer))
+        from .generic import layers_get
+
+        mods = [layers_get(layer["layer_type"])(in_chan=hid_chan, **layer) for _, layer in layers.items()]
         self.globalatt = nn.Sequential(*mods)
         self.fusion_layers = nn.ModuleList([InjectionMultiSum(hid_chan, kernel_size, norm_type, is2d) for _ in range(upsampling_depth)])
         self.concat_layers = nn.ModuleList([InjectionMultiSum(hid_chan, kernel_size, norm_type, is2d) for _ in range(upsampling_depth - 1)])
@@ -361,13 +345,14 @@ class TDANet(nn.Module):
     def __init__(self, in_chan=-1, hid_chan=-1, kernel_size=5, stride=2, norm_type="gLN", act_type="PReLU", upsampling_depth=4,
                  layers=dict(), repeats=4, shared=False, is2d=False, *args, **kwargs):
         super().__init__()
-        if not shared:
-            raise NotImplementedError("RTFS-Net configurations share one block across repeats (shared: true)")
+        if not shared and is2d:
+            raise NotImplementedError("the 2-D block kernels serve the RTFS-Net configurations, which share one block across repeats (shared: true)")
         self.repeats, self.shared, self.is2d = repeats, shared, is2d
-        self.blocks = TDANetBlock(in_chan, hid_chan, kernel_size, stride, norm_type, act_type, upsampling_depth, layers, is2d)
+        mk = lambda: TDANetBlock(in_chan, hid_chan, kernel_size, stride, norm_type, act_type, upsampling_depth, layers, is2d)
+        self.blocks = mk() if shared else nn.ModuleList(mk() for _ in range(repeats))  # separators/tdanet.py:168-205
 
     def get_block(self, i):
-        return self.blocks
+        return self.blocks if self.shared else self.blocks[i]
 
     def forward(self, x):
         residual = x
@@ -412,16 +397,27 @@ class MultiModalFusion(nn.Module):
 
     def __init__(self, audio_bn_chan, video_bn_chan, kernel_size=1, fusion_repeats=3, fusion_type="ConcatFusion", fusion_shared=False, is2d=False, **kwargs):
         super().__init__()
-        if fusion_type != "ATTNFusion" or not fusion_shared or fusion_repeats != 1:
-            raise NotImplementedError("only the RTFS-Net CAF fusion (ATTNFusion, shared, fusion_repeats = 1) is on the hot path")
-        self.fusion_repeats = fusion_repeats
-        self.fusion_module = ATTNFusion(audio_bn_chan, video_bn_chan, kernel_size, video_fusion=fusion_repeats > 1, is2d=is2d, **kwargs)
+        from .generic import fusion_get
+
+        self.fusion_repeats, self.fusion_type, self.fusion_shared, self.is2d = fusion_repeats, fusion_type, fusion_shared, is2d
+        cls = fusion_get(fusion_type) if fusion_repeats > 0 else nn.Identity
+        if cls is ATTNFusion and (not fusion_shared or fusion_repeats != 1):
+            raise NotImplementedError("the CAF kernels serve the RTFS-Net form of ATTNFusion (shared, fusion_repeats = 1)")
+        mk = lambda vf: cls(ain_chan=audio_bn_chan, vin_chan=video_bn_chan, kernel_size=kernel_size, video_fusion=vf, is2d=is2d, **kwargs)
+        if fusion_shared:
+            self.fusion_module = mk(fusion_repeats > 1)
+        else:  # TDAVNet/fusion.py:250-262: the last fusion does not feed the video stream
+            self.fusion_module = nn.ModuleList(mk(i != fusion_repeats - 1) for i in range(fusion_repeats))
 
     def get_fusion_block(self, i):
-        return self.fusion_module
+        return self.fusion_module if self.fusion_shared else self.fusion_module[i]
 
     def forward(self, audio, video):
-        return self.fusion_module(audio, video)[0]
+        a_res, v_res = audio, video
+        a = v = None
+        for i in range(self.fusion_repeats):  # TDAVNet/fusion.py:270-281
+            a, v = self.get_fusion_block(i)(audio, video) if i == 0 else self.get_fusion_block(i)(a + a_res, v + v_res)
+        return a
 
 
 class RefinementModule(nn.Module):
@@ -432,19 +428,52 @@ class RefinementModule(nn.Module):
         self.audio_params, self.video_params, self.fusion_params = audio_params, video_params, fusion_params
         self.fusion_repeats = video_params.get("repeats", 0)
         self.audio_repeats = audio_params["repeats"] - self.fusion_repeats
-        for p, key in ((audio_params, "audio_net"), (video_params, "video_net")):
-            if p.get(key) != "TDANet":
-                raise NotImplementedError(f"{key}={p.get(key)} is outside the RTFS-Net hot path")
-        self.audio_net = TDANet(**audio_params, in_chan=audio_bn_chan)
-        self.video_net = TDANet(**video_params, in_chan=video_bn_chan)
+        from .generic import separators_get
+
+        self.audio_net = separators_get(audio_params.get("audio_net", None))(**audio_params, in_chan=audio_bn_chan)
+        self.video_net = separators_get(video_params.get("video_net", None))(**video_params, in_chan=video_bn_chan)
         self.crossmodal_fusion = MultiModalFusion(**fusion_params, audio_bn_chan=audio_bn_chan, video_bn_chan=video_bn_chan, fusion_repeats=self.fusion_repeats)
+        # CUDA path: the RTFS-Net form (2-D shared TDANet audio block, CAF fusion once); anything else runs the eager schedule below
+        self.fast = bool(getattr(self.audio_net, "is2d", False)) and isinstance(self.audio_net, TDANet) and \
+            isinstance(self.crossmodal_fusion.get_fusion_block(0) if self.fusion_repeats > 0 else None, ATTNFusion)
+        if bool(getattr(self.audio_net, "is2d", False)) and not self.fast:
+            raise NotImplementedError("2-D audio blocks are served by the CUDA path only in the RTFS-Net form (TDANet is2d + ATTNFusion, fusion_repeats = 1)")
         self._rt = None
 
     def forward(self, audio, video):
-        return self._rt().refine(audio, video)
+        if self.fast:
+            return self._rt().refine(audio, video)
+        a_res, v_res = audio, video  # TDAVNet/refinement_module.py:45-62, eager (1-D configurations)
+        for i in range(self.fusion_repeats):
+            audio = self.audio_net.get_block(i)(audio + a_res if i > 0 else audio)
+            video = self.video_net.get_block(i)(video + v_res if i > 0 else video)
+            audio, video = self.crossmodal_fusion.get_fusion_block(i)(audio, video)
+        for j in range(self.audio_repeats):
+            i = j + self.fusion_repeats
+            audio = self.audio_net.get_block(i)(audio + a_res if i > 0 else audio)
+        return audio
 
     def get_MACs(self, bn_audio, bn_video):
-        return [0, 0, 0, 0, 0, 0]
+        """[MACs (M), params (K)] of audio_net, video_net and crossmodal_fusion, in the reference's order
+        (TDAVNet/refinement_module.py:74-83).  The fused audio path is counted in closed form, eager
+        modules with forward hooks (generic.count_macs) instead of thop."""
+        from .generic import count_macs
+
+        out = []
+        if self.fast:
+            T, Fq = bn_audio.shape[-2], bn_audio.shape[-1]
+            out += [int(self.audio_params["repeats"] * rtfs_block_macs(T, Fq) / 1e6), int(sum(p.numel() for p in self.audio_net.parameters()) / 1e3)]
+            m, p = count_macs(self.video_net.get_block(0), (bn_video.float().cpu(),)) if next(self.video_net.parameters()).device.type == "cpu" else \
+                count_macs(self.video_net.get_block(0), (bn_video,))
+            out += [int(m * self.fusion_repeats / 1e6), int(sum(q.numel() for q in self.video_net.parameters()) / 1e3)]
+            Tv = bn_video.shape[-1]
+            caf = T * Fq * 256 * 2 + Tv * (256 * 2 + 1024 * 2)
+            out += [int(caf / 1e6), int(sum(q.numel() for q in self.crossmodal_fusion.parameters()) / 1e3)]
+            return out
+        for mod, inp in ((self.audio_net, (bn_audio,)), (self.video_net, (bn_video,)), (self.crossmodal_fusion, (bn_audio, bn_video))):
+            m, p = count_macs(mod, inp)
+            out += [int(m / 1e6), int(p / 1e3)]
+        return out
 
 
 class STFTEncoder(nn.Module):
@@ -488,15 +517,46 @@ class MaskGenerator(nn.Module):
     def __init__(self, n_src, audio_emb_dim, bottleneck_chan, kernel_size=1, mask_act="ReLU", RI_split=False, output_gate=False,
                  dw_gate=False, direct=False, is2d=False, *args, **kwargs):
         super().__init__()
-        if not (n_src == 1 and audio_emb_dim == 256 and bottleneck_chan == 256 and kernel_size == 1 and mask_act == "ReLU" and RI_split
-                and not output_gate and not direct and is2d):
-            raise NotImplementedError("the mask kernel is built for the RTFS-Net S^3 head (RI_split, ReLU, n_src 1)")
-        self.n_src = n_src
-        self.mask_generator = nn.Sequential(nn.PReLU(), ConvNormAct(bottleneck_chan, n_src * audio_emb_dim, kernel_size, act_type=mask_act, is2d=is2d))
+        self.fast = bool(n_src == 1 and audio_emb_dim == 256 and bottleneck_chan == 256 and kernel_size == 1 and mask_act == "ReLU" and RI_split
+                         and not output_gate and not direct and is2d)
+        if is2d and not self.fast:
+            raise NotImplementedError("the 2-D mask kernel is built for the RTFS-Net S^3 head (RI_split, ReLU, n_src 1, 256 channels)")
+        self.n_src, self.in_chan, self.RI_split, self.output_gate, self.direct = n_src, audio_emb_dim, RI_split, output_gate, direct
+        if not direct:
+            chan = n_src * audio_emb_dim
+            self.mask_generator = nn.Sequential(nn.PReLU(), ConvNormAct(bottleneck_chan, chan, kernel_size, act_type=mask_act, is2d=is2d))
+            if output_gate:
+                groups = chan if dw_gate else 1
+                self.output = ConvNormAct(chan, chan, 1, act_type="Tanh", is2d=is2d, groups=groups)
+                self.gate = ConvNormAct(chan, chan, 1, act_type="Sigmoid", is2d=is2d, groups=groups)
         self._rt = None
 
     def forward(self, refined_features, audio_mixture_embedding):
-        return self._rt().mask(refined_features, audio_mixture_embedding)
+        if self.fast:
+            return self._rt().mask(refined_features, audio_mixture_embedding)
+        if self.direct:  # 1-D configurations (CTCNet), eager: mask_generator.py:84-99
+            return refined_features
+        m = self.mask_generator(refined_features)
+        if self.output_gate:
+            m = self.output(m) * self.gate(m)
+        e = audio_mixture_embedding
+        B, dims = e.shape[0], tuple(e.shape[-(e.ndim // 2):])
+        if self.RI_split:
+            m = m.view(B, self.n_src, 2, self.in_chan // 2, *dims)
+            e = e.view(B, 2, self.in_chan // 2, *dims)
+            mr, mi, er, ei = m[:, :, 0], m[:, :, 1], e[:, 0].unsqueeze(1), e[:, 1].unsqueeze(1)
+            return torch.cat([er * mr - ei * mi, er * mi + ei * mr], 2)
+        return m.view(B, self.n_src, self.in_chan, *dims) * e.unsqueeze(1)
+
+
+def rtfs_block_macs(T, Fq):
+    """Multiply-accumulates of one RTFS block pass on a (256, T, Fq) input."""
+    Tc, Fc = (T - 2) // 2 + 1, 64
+    P, Pc = T * Fq, Tc * Fc
+    blk = 2 * P * 256 * 64 + 3 * P * 64 * 16 + 8 * Pc * 64 * 16
+    for S, O in ((Fc, Tc), (Tc, Fc)):
+        blk += O * (S - 7) * (512 * 256 + 3 * 64 * 192 + 64 * 512)
+    return blk + Pc * 64 * 96 + 4 * Tc * Tc * (256 + 1024) + Pc * 64 * 64
 
 
 # =============================================================================== runtime
@@ -807,28 +867,36 @@ class AVNet(BaseAVModel):
         self.enc_dec_params, self.audio_params, self.video_params = dict(enc_dec_params), dict(audio_params), dict(video_params)
         self.fusion_params, self.mask_generation_params = dict(fusion_params), dict(mask_generation_params)
         self.print_macs = print_macs
-        if self.enc_dec_params.get("encoder_type") != "STFTEncoder" or self.enc_dec_params.get("decoder_type") != "STFTDecoder":
-            raise NotImplementedError("only the STFT encoder/decoder of the RTFS-Net configurations is on the hot path")
-        self.encoder = STFTEncoder(**self.enc_dec_params, in_chan=1, upsampling_depth=self.audio_params.get("upsampling_depth", 1))
+        from .generic import decoder_get, encoder_get, mask_generator_get
+
+        # tdavnet.py:37-84, string-keyed as in the reference.  STFT encoder => the RTFS-Net CUDA path (every component must then
+        # be in its RTFS-Net form: the constructors below raise otherwise -- there is no eager fallback on that path); any other
+        # encoder => the 1-D family (CTCNet) as plain PyTorch modules (generic.py), an API-compatibility path.
+        self.fast = self.enc_dec_params.get("encoder_type") == "STFTEncoder"
+        self.encoder = encoder_get(self.enc_dec_params["encoder_type"])(**self.enc_dec_params, in_chan=1, upsampling_depth=self.audio_params.get("upsampling_depth", 1))
         self.enc_out_chan = self.encoder.get_out_chan()
         self.mask_generation_params["mask_generator_type"] = self.mask_generation_params.get("mask_generator_type", "MaskGenerator")
-        if self.mask_generation_params["mask_generator_type"] != "MaskGenerator":
-            raise NotImplementedError(self.mask_generation_params["mask_generator_type"])
         self.audio_bn_chan = self.audio_bn_params.get("out_chan", self.enc_out_chan)
         self.audio_bn_params["out_chan"] = self.audio_bn_chan
         self.video_bn_chan = self.video_bn_params.get("out_chan", self.pretrained_vout_chan)
         self.audio_bottleneck = ConvNormAct(**self.audio_bn_params, in_chan=self.enc_out_chan)
         self.video_bottleneck = ConvNormAct(**self.video_bn_params, in_chan=self.pretrained_vout_chan)
-        bn = self.audio_bn_params
-        if not (bn.get("pre_norm_type") == "gLN" and bn.get("pre_act_type") == "ReLU" and bn.get("kernel_size") == 1 and bn.get("is2d")
-                and self.audio_bn_chan == 256 and bn.get("norm_type") is None and bn.get("act_type") is None):
-            raise NotImplementedError("the bottleneck kernel is built for gLN -> ReLU -> 1x1 conv 256 -> 256")
-        if self.video_bn_params.get("kernel_size", -1) > 0:
-            raise NotImplementedError("a non-identity video bottleneck is outside the RTFS-Net configurations")
+        if self.fast:
+            bn = self.audio_bn_params
+            if not (bn.get("pre_norm_type") == "gLN" and bn.get("pre_act_type") == "ReLU" and bn.get("kernel_size") == 1 and bn.get("is2d")
+                    and self.audio_bn_chan == 256 and bn.get("norm_type") is None and bn.get("act_type") is None):
+                raise NotImplementedError("the bottleneck kernel is built for gLN -> ReLU -> 1x1 conv 256 -> 256")
+            if self.video_bn_params.get("kernel_size", -1) > 0:
+                raise NotImplementedError("a non-identity video bottleneck is outside the RTFS-Net configurations")
+            if self.enc_dec_params.get("decoder_type") != "STFTDecoder":
+                raise NotImplementedError("the STFT encoder pairs with the STFT decoder on the CUDA path")
         self.refinement_module = RefinementModule(fusion_params=self.fusion_params, audio_params=self.audio_params, video_params=self.video_params,
                                                   audio_bn_chan=self.audio_bn_chan, video_bn_chan=self.video_bn_chan)
-        self.mask_generator = MaskGenerator(**self.mask_generation_params, n_src=self.n_src, audio_emb_dim=self.enc_out_chan, bottleneck_chan=self.audio_bn_chan)
-        self.decoder = STFTDecoder(**self.enc_dec_params, in_chan=self.enc_out_chan * self.n_src, n_src=self.n_src)
+        self.mask_generator = mask_generator_get(self.mask_generation_params["mask_generator_type"])(
+            **self.mask_generation_params, n_src=self.n_src, audio_emb_dim=self.enc_out_chan, bottleneck_chan=self.audio_bn_chan)
+        self.decoder = decoder_get(self.enc_dec_params["decoder_type"])(**self.enc_dec_params, in_chan=self.enc_out_chan * self.n_src, n_src=self.n_src)
+        if self.fast and not (self.refinement_module.fast and self.mask_generator.fast):
+            raise NotImplementedError("STFT-domain configurations are served by the CUDA path in their RTFS-Net form only")
 
         rt = _Runtime(self)
         object.__setattr__(self, "_runtime", rt)
@@ -836,12 +904,17 @@ class AVNet(BaseAVModel):
         for m in self.modules():
             if hasattr(m, "_rt"):
                 object.__setattr__(m, "_rt", getter)
-        object.__setattr__(self.audio_bottleneck, "_fused", rt.bottleneck)
+        if self.fast:
+            object.__setattr__(self.audio_bottleneck, "_fused", rt.bottleneck)
         if self.print_macs:
             self.get_MACs()
 
     def forward(self, audio_mixture, mouth_embedding=None):
-        return self._runtime.forward(audio_mixture, mouth_embedding)
+        if self.fast:
+            return self._runtime.forward(audio_mixture, mouth_embedding)
+        emb = self.encoder(audio_mixture)  # tdavnet.py:86-97, eager (1-D configurations)
+        refined = self.refinement_module(self.audio_bottleneck(emb), self.video_bottleneck(mouth_embedding))
+        return self.decoder(self.mask_generator(refined, emb), audio_mixture.shape)
 
     def get_config(self):
         return dict(n_src=self.n_src, pretrained_vout_chan=self.pretrained_vout_chan, enc_dec_params=self.enc_dec_params,
@@ -849,22 +922,44 @@ class AVNet(BaseAVModel):
                     video_params=self.video_params, fusion_params=self.fusion_params, mask_generation_params=self.mask_generation_params)
 
     def get_MACs(self):
-        """Analytic MAC count of the audio path at the reference's convention (B=1, 2 s, 50 frames;
-        base_av_model.py:61-118) -- closed form, no forward pass is run."""
-        T, Fq = 2 * 16000 // 128 + 1, 129
-        Tc, Fc = (T - 2) // 2 + 1, 64
-        P, Pc = T * Fq, Tc * Fc
-        R = self.audio_params["repeats"]
-        blk = 2 * P * 256 * 64 + 3 * P * 64 * 16 + 8 * Pc * 64 * 16
-        for S, O in ((Fc, Tc), (Tc, Fc)):
-            Lr = S - 7
-            blk += O * Lr * (512 * 256 + 3 * 64 * 192 + 64 * 512)
-        blk += Pc * 64 * 96 + 4 * Tc * Tc * (256 + 1024) + Pc * 64 * 64
-        macs = dict(encoder=P * 18 * 256, audio_bn=P * 256 * 256, audio_net=R * blk, mask=P * 256 * 256, decoder=P * 18 * 256)
-        total = sum(macs.values())
-        params = sum(p.numel() for p in self.parameters())
-        self.macs_parms = "RTFS-Net (audio path, analytic)\n" + "".join(f"{k:<12} MACs: {v / 1e6:>10.1f} M\n" for k, v in macs.items()) + \
-            f"Total ------ MACs: {total / 1e6:>10.1f} M    Params: {params / 1e3:>8.1f} K\n"
+        """MAC / parameter table at the reference's convention (B = 1, 2 s of audio, 50 video frames; base_av_model.py:61-118).
+        CUDA path: closed form for the fused audio stages, forward hooks for the eager video block -- no
+        CPU forward of the audio path is run; 1-D configurations: forward hooks on the eager modules (generic.count_macs)."""
+        from .generic import count_macs
+
+        params = lambda m: sum(p.numel() for p in m.parameters())
+        dev = next(self.parameters()).device
+        v_chan = self.pretrained_vout_chan if self.pretrained_vout_chan > 0 else 1
+        video = torch.rand(1, v_chan, 50, device=dev)
+        if self.fast:
+            T, Fq = 2 * 16000 // 128 + 1, 129
+            P = T * Fq
+            R = self.audio_params["repeats"]
+            macs = dict(encoder=P * 18 * 256, audio_bn=P * 256 * 256, audio_net=R * rtfs_block_macs(T, Fq), mask=P * 256 * 256, decoder=P * 18 * 256)
+            with torch.no_grad():
+                rm = self.refinement_module.get_MACs(torch.empty(1, 256, T, Fq, device="meta"), video)
+            rows = [("Encoder", macs["encoder"], params(self.encoder)), ("Audio BN", macs["audio_bn"], params(self.audio_bottleneck)),
+                    ("Video BN", 0, params(self.video_bottleneck)), ("   AudioNet", rm[0] * 1e6, rm[1] * 1e3), ("   VideoNet", rm[2] * 1e6, rm[3] * 1e3),
+                    ("   FusionNet", rm[4] * 1e6, rm[5] * 1e3), ("Mask Generator", macs["mask"], params(self.mask_generator)),
+                    ("Decoder", macs["decoder"], params(self.decoder))]
+        else:
+            audio = torch.rand(1, 2 * 16000, device=dev)
+            was_training = self.training
+            self.eval()
+            with torch.no_grad():
+                emb = self.encoder(audio)
+                bn_a, bn_v = self.audio_bottleneck(emb), self.video_bottleneck(video)
+                sep = self.mask_generator(bn_a, emb)
+                rm = self.refinement_module.get_MACs(bn_a, bn_v)
+                rows = [("Encoder",) + count_macs(self.encoder, (audio,)), ("Audio BN",) + count_macs(self.audio_bottleneck, (emb,)),
+                        ("Video BN",) + count_macs(self.video_bottleneck, (video,)), ("   AudioNet", rm[0] * 1e6, rm[1] * 1e3),
+                        ("   VideoNet", rm[2] * 1e6, rm[3] * 1e3), ("   FusionNet", rm[4] * 1e6, rm[5] * 1e3),
+                        ("Mask Generator",) + count_macs(self.mask_generator, (bn_a, emb)), ("Decoder",) + count_macs(self.decoder, (sep, audio.shape))]
+            self.train(was_training)
+            macs = {k.strip().lower().replace(" ", "_"): v for k, v, _ in rows}
+        total = sum(v for k, v, _ in rows)
+        self.macs_parms = "".join(f"{k + ' ':-<22} MACs: {v / 1e6:>10.1f} M    Params: {p / 1e3:>8.1f} K\n" for k, v, p in rows) + \
+            f"{'Total ':-<22} MACs: {total / 1e6:>10.1f} M    Params: {params(self) / 1e3:>8.1f} K\n"
         if self.print_macs:
             print(self.macs_parms)
         return macs

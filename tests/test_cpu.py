@@ -120,15 +120,32 @@ def test_registry():
 
 
 def test_unsupported_configs_fail_loudly():
+    """STFT-domain (CUDA path) configurations outside the RTFS-Net form raise instead of falling back to eager modules."""
     from rtfs_net_b200 import AVNet
 
     conf = audionet_conf(4)
-    conf["enc_dec_params"]["encoder_type"] = "ConvolutionalEncoder"
-    with pytest.raises(NotImplementedError):
+    conf["enc_dec_params"]["decoder_type"] = "ConvolutionalDecoder"  # STFT encoder with a 1-D decoder
+    with pytest.raises((NotImplementedError, TypeError)):
         AVNet(print_macs=False, **conf)
     conf = audionet_conf(4)
     conf["audio_params"]["layers"]["layer_1"]["rnn_type"] = "LSTM"
     with pytest.raises(NotImplementedError):
+        AVNet(print_macs=False, **conf)
+    conf = audionet_conf(4)
+    conf["audio_params"]["shared"] = False  # non-shared 2-D blocks
+    with pytest.raises(NotImplementedError):
+        AVNet(print_macs=False, **conf)
+    conf = audionet_conf(4)
+    conf["fusion_params"]["fusion_type"] = "ConcatFusion"  # 2-D audio block with a non-CAF fusion
+    with pytest.raises(NotImplementedError):
+        AVNet(print_macs=False, **conf)
+    conf = audionet_conf(4)
+    conf["audio_params"]["layers"]["layer_3"]["layer_type"] = "CBAMBlock"  # exists in the reference, out of scope here
+    with pytest.raises(NotImplementedError):
+        AVNet(print_macs=False, **conf)
+    conf = audionet_conf(4)
+    conf["audio_params"]["audio_net"] = "NoSuchNet"
+    with pytest.raises(ValueError):
         AVNet(print_macs=False, **conf)
 
 
