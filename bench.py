@@ -119,7 +119,7 @@ def stage_bytes(B):
         "RTFS_SG_ATT_QKV": 2.5 * G, "RTFS_SG_ATT_CORE": 2.5 * G, "RTFS_SG_ATT_PROJ": 3 * G,
         "RTFS_SG_TFAR_GLOBAL": 3.5 * G, "RTFS_SG_TFAR_LE0": 2 * H, "RTFS_SG_TFAR_CAT_GLOBAL": 5 * G,
         "RTFS_SG_TFAR_CAT_LOCAL": 2 * H + 2 * G, "RTFS_SG_RESID_OUT": resid_mid, "RTFS_SG_RESID_OUT_CAF": 2 * A + 2 * H + 2 * G,
-        "RTFS_SG_CAF_APPLY": 3 * A, "RTFS_SG_MASK": 3 * A, "RTFS_SG_DEC_GEMM": A * (1 + 18 / 256),
+        "RTFS_SG_CAF_APPLY": 3 * A, "RTFS_SG_MASK": 3 * A, "RTFS_SG_DEC_GEMM": A * (1 + 18 / 256), "RTFS_SG_MASK_DEC": A * (2 + 18 / 256),
     }, (4 * A + 14 * H + 36 * G), ((6 + 4 * REPEATS) * A + 14 * REPEATS * H + 36 * REPEATS * G)
 
 
@@ -406,7 +406,7 @@ def run_gpu(args):
             v["gbps"] = sbytes[k] / (v["ms_per_launch"] * 1e-3) / 1e9
     achieved = sbytes.get(top, 0.0) / (per_stage[top]["ms_per_launch"] * 1e-3) / 1e9
     block_stage_names = [n for n in _lib.STAGE_NAMES if n not in ("RTFS_SG_STFT", "RTFS_SG_ENC_CONV", "RTFS_SG_BOTTLENECK", "RTFS_SG_CAF_VIDEO",
-                                                                   "RTFS_SG_CAF_APPLY", "RTFS_SG_MASK", "RTFS_SG_DEC_GEMM", "RTFS_SG_DEC_ISTFT")]
+                                                                   "RTFS_SG_CAF_APPLY", "RTFS_SG_MASK", "RTFS_SG_DEC_GEMM", "RTFS_SG_DEC_ISTFT", "RTFS_SG_MASK_DEC")]
     block_ms = sum(per_stage[n]["ms_per_step"] for n in block_stage_names if n in per_stage) / REPEATS
     stage_sum = sum(v["ms_per_step"] for v in per_stage.values())
 

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RTFS_ABI_VERSION 6
+#define RTFS_ABI_VERSION 7
 #define RTFS_F 129
 #define RTFS_FC 64
 
@@ -90,6 +90,9 @@ enum rtfs_param {
     RTFS_P_AT_WQKVT, /* [64][96] */
     RTFS_P_AT_WOT,   /* [64][64] */
     RTFS_P_DEC_WE,   /* [256][32]: decoder weight in the encoder-conv layout, k = (i*3+j)*2 + o (dz = conv2d(dy, W_dec)) */
+    /* fused S^3 mask + decoder epilogue: [256][20], row = interleaved GEMM column (2c: channel c, 2c+1: channel c+128),
+     * entries 0..17 = RTFS_P_DEC_W[:, channel], 18..19 = 0 */
+    RTFS_P_DEC_WT,
     RTFS_P_COUNT
 };
 
@@ -129,6 +132,7 @@ enum rtfs_stage {
     RTFS_SG_CAF_VIDEO, RTFS_SG_CAF_APPLY, RTFS_SG_MASK, RTFS_SG_DEC_GEMM, RTFS_SG_DEC_ISTFT,
     RTFS_SG_DPRNN_FUSED, /* one launch per dual-path RNN (dprnn_fused.cuh) instead of PREP..CONVT */
     RTFS_SG_RESID_OUT_CAF, /* residual conv of the first block pass with the CAF fusion in its epilogue (addend aliases x) */
+    RTFS_SG_MASK_DEC,      /* S^3 mask with the decoder's 256 -> 18 contraction in its epilogue (z never written) */
     RTFS_SG_COUNT
 };
 

@@ -781,11 +781,22 @@ int run_mask(const Ctx& c, const float* refined, const float* a0, float* z, floa
     return 0;
 }
 
+// S^3 mask with the decoder's 256 -> 18 contraction in its epilogue: refined, a0 -> Q18 (workspace); z is never written
+int run_mask_dec(const Ctx& c, const float* refined, const float* a0) {
+    const Dims& d = c.d;
+    PreluLoader al{refined, c.P[RTFS_P_MK_A], 256};
+    MaskDecEpi4 ep{c.buf(RTFS_WS_Q18), c.P[RTFS_P_MK_B], a0, c.P[RTFS_P_DEC_WT]};
+    STAGE(RTFS_SG_MASK_DEC);
+    CK((launch_gemm_tcp<256, 256, 3, 3, false, 4, 2, 512>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
+    return 0;
+}
+
+// z == nullptr: the partial products Q18 are already in the workspace (run_mask_dec)
 int run_decoder(const Ctx& c, const float* z, float* wav_out, int L) {
     const Dims& d = c.d;
-    PlainLoader al{z, 256, 256};
-    StoreEpi ep{c.buf(RTFS_WS_Q18), 18, nullptr};
-    {
+    if (z != nullptr) {
+        PlainLoader al{z, 256, 256};
+        StoreEpi ep{c.buf(RTFS_WS_Q18), 18, nullptr};
         STAGE(RTFS_SG_DEC_GEMM);
         CK((launch_gemm<32, 256, true>(al, c.P[RTFS_P_DEC_W], ep, (int)(d.B * d.P), 18, c.st)));
     }
@@ -929,8 +940,14 @@ int rtfs_avnet_forward(const float* const* params, const float* wav, const float
         cur = other;
         other = t;
     }
-    RUN(run_mask(c, cur, a0, a1));  // a1 is dead by now: reuse it for z
-    RUN(run_decoder(c, a1, out, L));
+    static const bool unfused_md = env_flag("RTFS_UNFUSED_MASK_DEC");  // A/B: mask writes z, the decoder GEMM reads it back
+    if (use_tc() && use_persistent(3) && !unfused_md) {
+        RUN(run_mask_dec(c, cur, a0));
+        RUN(run_decoder(c, nullptr, out, L));
+    } else {
+        RUN(run_mask(c, cur, a0, a1));  // a1 is dead by now: reuse it for z
+        RUN(run_decoder(c, a1, out, L));
+    }
     return 0;
 }
 

@@ -423,6 +423,103 @@ struct MaskEpi4T {
 };
 using MaskEpi4 = MaskEpi4T<false>;
 
+constexpr int TC_STG_LD = 36;  // floats per staged epilogue row (32 + 4 pad)
+
+// S^3 mask + decoder contraction in one epilogue (mask_generator.py:67-99 + decoder.py:110-116): the masked embedding z is never
+// written.  Every 32 x 32 block of z goes back into the warp's staging tile; then thread = row accumulates the 18 partial
+// products of the transposed 3x3 conv (ConvTranspose2d 256 -> 2: o*9 + i*3 + j) for its row in fp32 against a shared-memory
+// copy of the decoder filter ([interleaved column][20]: all lanes read the same entry -> broadcast); the two column halves of a
+// row are combined through the staging tile and Q18 (7 % of a 256-channel tensor) is the only output.
+struct MaskDecEpi4 {
+    float* q18;          // [M][18]
+    const float* bias;   // [256] interleaved like the GEMM columns
+    const float* a0;     // encoder output [M][256]
+    const float* wdec;   // [256][20] decoder filter, rows in interleaved column order, 18 taps + 2 zeros (weights.py: RTFS_P_DEC_WT)
+    static constexpr int kTcpEpiRegs = 104;
+    static constexpr bool kRollPre = false;
+    static constexpr bool kFusedRows = true;
+    static constexpr int kSmemBytes = 256 * 20 * 4;
+    struct Pre {
+        float2 er, ei;
+    };
+    float4 bi_;
+    const float* wtab_;
+    float2 q_[9];  // the 18 partial products of this thread's row, packed for f32x2 FMAs
+    DEVINL void bind_smem(float* tab, int tid, int nthr) {
+        for (int i = tid; i < 256 * 5; i += nthr) reinterpret_cast<float4*>(tab)[i] = ldg4(wdec + 4 * i);
+        wtab_ = tab;
+    }
+    DEVINL void init(int, int) {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) q_[r] = make_float2(0.f, 0.f);
+    }
+    DEVINL void prep(int col) { bi_ = ldg4(bias + col); }
+    DEVINL Pre load(int row, int col) const {
+        const long long o = (long long)row * 256 + (col >> 1);
+        Pre p;
+        p.er = ldg2(a0 + o);
+        p.ei = ldg2(a0 + o + 128);
+        return p;
+    }
+    // z piece of (row, interleaved columns col..col+3) = (re c, im c, re c+1, im c+1) -> the staging slot it came from
+    DEVINL void store4s(int, int, float4 v, const Pre& p, float* slot) {
+        const float4 bi = bi_;
+        const float mr0 = fmaxf(v.x + bi.x, 0.f), mi0 = fmaxf(v.y + bi.y, 0.f);
+        const float mr1 = fmaxf(v.z + bi.z, 0.f), mi1 = fmaxf(v.w + bi.w, 0.f);
+        const float2 er = p.er, ei = p.ei;
+        *reinterpret_cast<float4*>(slot) = make_float4(er.x * mr0 - ei.x * mi0, er.x * mi0 + ei.x * mr0, er.y * mr1 - ei.y * mi1, er.y * mi1 + ei.y * mr1);
+    }
+    // thread = row: 32 staged z values of this block against the filter rows col0 .. col0 + 31 (9 packed FMAs per value)
+    DEVINL void block_reduce(const float* zrow, int col0) {
+        const float4* w = reinterpret_cast<const float4*>(wtab_ + col0 * 20);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 z4 = *reinterpret_cast<const float4*>(zrow + 4 * j4);
+            const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const float4* wr = w + (4 * j4 + jj) * 5;
+                const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
+                const float2 w4 = *reinterpret_cast<const float2*>(wr + 4);
+                const float2 z = make_float2(zz[jj], zz[jj]);
+                q_[0] = __ffma2_rn(z, make_float2(w0.x, w0.y), q_[0]);
+                q_[1] = __ffma2_rn(z, make_float2(w0.z, w0.w), q_[1]);
+                q_[2] = __ffma2_rn(z, make_float2(w1.x, w1.y), q_[2]);
+                q_[3] = __ffma2_rn(z, make_float2(w1.z, w1.w), q_[3]);
+                q_[4] = __ffma2_rn(z, make_float2(w2.x, w2.y), q_[4]);
+                q_[5] = __ffma2_rn(z, make_float2(w2.z, w2.w), q_[5]);
+                q_[6] = __ffma2_rn(z, make_float2(w3.x, w3.y), q_[6]);
+                q_[7] = __ffma2_rn(z, make_float2(w3.z, w3.w), q_[7]);
+                q_[8] = __ffma2_rn(z, w4, q_[8]);
+            }
+        }
+    }
+    // combine the two column halves of a row (warps q and q + 4) through the upper half's staging tile and store Q18
+    DEVINL void tile_done(float* stg_all, int warp, int lane, int row, int M) {
+        const int q = warp & 3, hlf = warp >> 2;
+        float* mine = stg_all + warp * (32 * TC_STG_LD) + lane * TC_STG_LD;
+        if (hlf == 1) {
+#pragma unroll
+            for (int r = 0; r < 9; ++r) *reinterpret_cast<float2*>(mine + 2 * r) = q_[r];
+        }
+        named_bar_sync(4 + q, 64);
+        if (hlf == 0) {
+            const float* other = stg_all + (warp + 4) * (32 * TC_STG_LD) + lane * TC_STG_LD;
+            if (row < M) {
+                float* dst = q18 + (long long)row * 18;
+#pragma unroll
+                for (int r = 0; r < 9; ++r) {
+                    const float2 o = *reinterpret_cast<const float2*>(other + 2 * r);
+                    *reinterpret_cast<float2*>(dst + 2 * r) = make_float2(q_[r].x + o.x, q_[r].y + o.y);
+                }
+            }
+        }
+        named_bar_sync(4 + q, 64);  // the upper half may reuse its staging tile
+    }
+    DEVINL void finish(float*) {}
+    DEVINL void finish_group(float*, int, int, int) {}
+};
+
 // ConvTranspose1d-as-GEMM epilogue of the dual-path RNN (rnn_layers.py:153-160)
 struct ConvTEpi4 {
     float* out;
@@ -461,7 +558,6 @@ struct ConvTEpi4 {
 constexpr int TC_BM = 128, TC_KC = 32, TC_THREADS = 256;
 constexpr int TC_LBO_A = TC_BM * 16 + 16;              // 2064 B between K-direction core matrices of A
 constexpr int TC_A_STAGE = 16640;                      // 8 * 2064 = 16512, rounded up to 128
-constexpr int TC_STG_LD = 36;                          // floats per staged epilogue row (32 + 4 pad)
 constexpr int TC_STG_BYTES = 8 * 32 * TC_STG_LD * 4;   // 8 warps x [32][36] floats
 
 template <int BN>
@@ -513,6 +609,24 @@ struct ep_roll {
 template <class EP>
 struct ep_roll<EP, decltype((void)EP::kRollPre)> {
     static constexpr bool value = EP::kRollPre;
+};
+
+// epilogues that consume whole rows through the staging tile (fused S^3 mask + decoder) and own a shared-memory table
+template <class EP, class = void>
+struct ep_fused_rows {
+    static constexpr bool value = false;
+};
+template <class EP>
+struct ep_fused_rows<EP, decltype((void)EP::kFusedRows)> {
+    static constexpr bool value = EP::kFusedRows;
+};
+template <class EP, class = void>
+struct ep_smem_bytes {
+    static constexpr int value = 0;
+};
+template <class EP>
+struct ep_smem_bytes<EP, decltype((void)EP::kSmemBytes)> {
+    static constexpr int value = EP::kSmemBytes;
 };
 
 template <class AL, class = void>

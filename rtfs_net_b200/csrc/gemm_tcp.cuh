@@ -46,7 +46,7 @@ DEVINL void mbar_arrive_cta(uint64_t* bar) {
 
 template <int BN, int KTOT, int NSA, int NSW, bool WRES>
 __host__ __device__ constexpr int tcp_smem_bytes(int extra_floats) {
-    return NSA * TC_A_STAGE + (WRES ? (KTOT / TC_KC) : NSW) * BN * 128 + TC_STG_BYTES + 2 * extra_floats * 4 + 512;
+    return NSA * TC_A_STAGE + (WRES ? (KTOT / TC_KC) : NSW) * BN * 128 + TC_STG_BYTES + 2 * extra_floats * 4 + 512;  // + ep_smem_bytes<EP> (launch)
 }
 
 // EPS: epilogue functor exposes finish_group(scratch, gtid, nthr, barid) (gLN statistics) instead of finish()
@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
     unsigned char* w_stage = a_stage + NSA * TC_A_STAGE;
     float* stg_all = reinterpret_cast<float*>(w_stage + NWS * WBYTES);
     float* extra = stg_all + TC_STG_BYTES / 4;  // two loader tables (ping-pong by tile)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(extra + 2 * AL::kExtra);
+    float* ep_tab = extra + 2 * AL::kExtra;  // epilogue-owned table (fused mask + decoder: the decoder filter)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ep_tab + ep_smem_bytes<EP>::value / 4);
     uint64_t* full_a = bars;                 // [NSA] count TCP_PROD
     uint64_t* empty_a = full_a + NSA;        // [NSA] count 1 (tcgen05.commit)
     uint64_t* full_w = empty_a + NSA;        // [NWS] count 1 + tx
@@ -128,6 +129,11 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
         // requested right after the matching rows of block n are stored -- same registers, but a warp no longer exposes one
         // memory round trip per block (4 per tile for the mask epilogue, which made the epilogue warps the critical path)
         constexpr bool ROLL = ep_roll<EP>::value && !AFF;
+        constexpr bool FUSED = ep_fused_rows<EP>::value;
+        if constexpr (FUSED) {
+            ep.bind_smem(ep_tab, tid, TCP_EPI);
+            named_bar_sync(3, TCP_EPI);
+        }
         typename std::conditional<AFF, typename ep_pre<EP>::type, typename EP::Pre>::type pre[8];
         if constexpr (ROLL) {
             if ((int)blockIdx.x < ntiles) {
@@ -190,7 +196,8 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
 #endif
                     const int row = rowq0 + r;
                     if (row < M) {
-                        if constexpr (AFF) ep.store_p(p, row, x, pre[p]);
+                        if constexpr (FUSED) ep.store4s(row, col0 + c4, x, pre[p], stg + r * TC_STG_LD + c4);
+                        else if constexpr (AFF) ep.store_p(p, row, x, pre[p]);
                         else ep.store4(row, col0 + c4, x, pre[p]);
                     }
                     if constexpr (ROLL) {
@@ -203,10 +210,15 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
                     }
                 }
                 __syncwarp();
+                if constexpr (FUSED) {
+                    ep.block_reduce(stg + lane * TC_STG_LD, col0);
+                    __syncwarp();
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cta(tmem_empty + acc);  // this warp's TMEM reads of the accumulator are complete
+            if constexpr (FUSED) ep.tile_done(stg_all, warp, lane, row0 + q * 32 + lane, M);
             ep.finish_group(scratch, tid, TCP_EPI, 1);
         }
     } else if (warp < MMA_WARP) {
@@ -474,7 +486,7 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
 template <int BN, int KTOT, int NSA, int NSW, bool WRES, int PF, int ASYNC, int NPROD, class AL, class EP>
 inline cudaError_t launch_gemm_tcp(const AL& al, const float* Wimg, const EP& ep, int M, cudaStream_t st) {
     auto kern = gemm_tcp_kernel<BN, KTOT, NSA, NSW, WRES, PF, ASYNC, NPROD, AL, EP>;
-    const int smem = tcp_smem_bytes<BN, KTOT, NSA, NSW, WRES>(AL::kExtra);
+    const int smem = tcp_smem_bytes<BN, KTOT, NSA, NSW, WRES>(AL::kExtra) + ep_smem_bytes<EP>::value;
     static SmemCfg cfg;  // per instantiation, per device
     if (cudaError_t e = ensure_smem(kern, smem, cfg); e != cudaSuccess) return e;
     const int ntiles = (M + TC_BM - 1) / TC_BM;

@@ -74,7 +74,7 @@ TRAIN_ONLY = ("RTFS_P_BN_WT", "RTFS_P_PJ_WT", "RTFS_P_RC_WT", "RTFS_P_MK_WT", "R
 # slots that are images / transposes of another slot: the backward returns no gradient for them (the base slot carries it)
 DERIVED = TRAIN_ONLY[:-1] + ("RTFS_P_BN_WI", "RTFS_P_PJ_WI", "RTFS_P_RC_WI", "RTFS_P_MK_WI", "RTFS_P_RF_WI0", "RTFS_P_RF_WI1", "RTFS_P_RF_WI2",
                              "RTFS_P_RF_WI3", "RTFS_P_RF_CTWI", "RTFS_P_RT_WI0", "RTFS_P_RT_WI1", "RTFS_P_RT_WI2", "RTFS_P_RT_WI3", "RTFS_P_RT_CTWI",
-                             "RTFS_P_RF_FUSED", "RTFS_P_RT_FUSED", "RTFS_P_ENC_WI3", "RTFS_P_AT_WQKVI", "RTFS_P_AT_WOI", "RTFS_P_DEC_W",
+                             "RTFS_P_RF_FUSED", "RTFS_P_RT_FUSED", "RTFS_P_ENC_WI3", "RTFS_P_AT_WQKVI", "RTFS_P_AT_WOI", "RTFS_P_DEC_W", "RTFS_P_DEC_WT",
                              "RTFS_P_WINDOW", "RTFS_P_COSTAB", "RTFS_P_SINTAB", "RTFS_P_CAF_SK", "RTFS_P_CAF_TK", "RTFS_P_CAF_SV", "RTFS_P_CAF_TV")
 
 
@@ -196,6 +196,7 @@ def prepare(sd, device, train=False):
     out["RTFS_P_MK_W"] = tf32_round(g("mask_generator.mask_generator.1.full_layer.2.weight").reshape(256, 256)[perm])
     out["RTFS_P_MK_B"] = g("mask_generator.mask_generator.1.full_layer.2.bias")[perm].contiguous()
     out["RTFS_P_DEC_W"] = g("decoder.decoder.weight").permute(1, 2, 3, 0).reshape(18, 256).contiguous()
+    out["RTFS_P_DEC_WT"] = torch.cat([out["RTFS_P_DEC_W"].t()[perm], torch.zeros(256, 2, device=device)], 1).contiguous()  # [interleaved col][20]
     if train:
         # W'[N = K_fwd][K = N_fwd] images for dX = dY * W
         out["RTFS_P_BN_WT"] = out["RTFS_P_BN_W"].t()
