@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RTFS_ABI_VERSION 7
+#define RTFS_ABI_VERSION 8
 #define RTFS_F 129
 #define RTFS_FC 64
 
@@ -93,6 +93,9 @@ enum rtfs_param {
     /* fused S^3 mask + decoder epilogue: [256][20], row = interleaved GEMM column (2c: channel c, 2c+1: channel c+128),
      * entries 0..17 = RTFS_P_DEC_W[:, channel], 18..19 = 0 */
     RTFS_P_DEC_WT,
+    /* VP (video) block, all parameters packed in the order of rtfs_video_pack_plan (eval BatchNorm folded; may be NULL when the
+     * host runs the video block with torch modules: training, Tv > 100, non-RTFS video configurations) */
+    RTFS_P_VIDEO_PACK,
     RTFS_P_COUNT
 };
 
@@ -133,6 +136,7 @@ enum rtfs_stage {
     RTFS_SG_DPRNN_FUSED, /* one launch per dual-path RNN (dprnn_fused.cuh) instead of PREP..CONVT */
     RTFS_SG_RESID_OUT_CAF, /* residual conv of the first block pass with the CAF fusion in its epilogue (addend aliases x) */
     RTFS_SG_MASK_DEC,      /* S^3 mask with the decoder's 256 -> 18 contraction in its epilogue (z never written) */
+    RTFS_SG_VIDEO,         /* VP block kernel (module-level call; timed by the host around rtfs_video_forward) */
     RTFS_SG_COUNT
 };
 
@@ -206,6 +210,12 @@ int rtfs_mask_forward(const float* const* params, const float* refined, const fl
 
 /* STFTDecoder.forward (TDAVNet/decoder.py:110-132): z (B,T,F,256) -> wav (B,L). */
 int rtfs_decoder_forward(const float* const* params, const float* z, float* wav_out, void* ws, int B, int L, void* stream);
+
+/* TDANetBlock.forward with is2d = False (separators/tdanet.py:106-133; GlobalAttention layers/attention.py:28-73,192-220): the VP
+ * block on the lip embedding, x (B,512,Tv) -> out (B,512,Tv), one kernel, inference (eval BatchNorm).  8 <= Tv <= 100. */
+int rtfs_video_forward(const float* const* params, const float* x, float* out, int B, int Tv, void* stream);
+/* Float offsets of the fields of RTFS_P_VIDEO_PACK (offsets[n_fields]); returns the total float count, *n_fields the field count. */
+int rtfs_video_pack_plan(int* offsets, int* n_fields);
 
 /* AVNet.forward (tdavnet.py:86-97) + RefinementModule.forward (TDAVNet/refinement_module.py:45-62)
  * for fusion_repeats = 1: wav (B,L), video = output of the video block (B,512,Tv) -> out (B,L).

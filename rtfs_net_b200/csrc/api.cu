@@ -17,6 +17,7 @@
 #include "gemm.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tcp.cuh"
+#include "video.cuh"
 
 using namespace rtfs;
 
@@ -915,6 +916,45 @@ int rtfs_decoder_forward(const float* const* params, const float* z, float* wav_
     Ctx c;
     if (!make_ctx(c, params, ws, B, L / 128 + 1, 0, stream)) return -2;
     return run_decoder(c, z, wav_out, L);
+}
+
+int rtfs_video_pack_plan(int* offsets, int* n_fields) {
+    const VpOffsets o = vp_offsets();
+    if (offsets)
+        for (int i = 0; i < VP_COUNT; ++i) offsets[i] = o.o[i];
+    if (n_fields) *n_fields = VP_COUNT;
+    return o.total;
+}
+
+int rtfs_video_forward(const float* const* params, const float* x, float* out, int B, int Tv, void* stream) {
+    if (params == nullptr || params[RTFS_P_VIDEO_PACK] == nullptr) return fail_msg("rtfs_video_forward: packed video parameters missing");
+    if (B < 1 || Tv < 8 || Tv > 100) return fail_msg("rtfs_video_forward: 8 <= Tv <= 100 frames");
+    VideoArgs a;
+    a.x = x;
+    a.w = params[RTFS_P_VIDEO_PACK];
+    a.out = out;
+    a.off = vp_offsets();
+    a.Tv = Tv;
+    int len = Tv, start = 0;
+    for (int i = 0; i < VP_DEPTH; ++i) {
+        a.len[i] = len;
+        a.start[i] = start;
+        start += len;
+        len = (len - 1) / 2 + 1;  // k = 3, stride 2, padding 1
+    }
+    a.sumlen = start;
+    const int smem = vp_smem_floats(Tv, a.sumlen) * 4;
+    if (smem > 227 * 1024) return fail_msg("rtfs_video_forward: shared-memory budget exceeded");
+    static SmemCfg cfg;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CKN(ensure_smem(video_block_kernel, smem, cfg));
+    {
+        struct { cudaStream_t st; } c{st};
+        STAGE(RTFS_SG_VIDEO);
+        video_block_kernel<<<B, 256, smem, st>>>(a);
+        CK(cudaGetLastError());
+    }
+    return 0;
 }
 
 int rtfs_avnet_forward(const float* const* params, const float* wav, const float* video, float* out, void* ws, int B, int L, int Tv, int repeats, void* stream) {

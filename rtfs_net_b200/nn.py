@@ -749,10 +749,19 @@ class _Runtime:
 
     # ---------------------------------------------------------------- video (VP) block
     def video_block(self, mouth):
-        """The VP block (tdanet.py:106-133 in 1-D, attention.py:9-73,192-220) is ~150 launch-bound torch library ops on
-        (B,512,Tv) tensors: captured once per (shape, parameter version) into a CUDA graph and replayed.
-        RTFS_NO_VIDEO_GRAPH=1 runs it eagerly."""
+        """The VP block (tdanet.py:106-133 in 1-D, attention.py:9-73,192-220): one hand-written kernel per call (csrc/video.cuh)
+        for the RTFS-Net video configuration and 8..100 frames.  Other shapes (and RTFS_TORCH_VIDEO=1, the A/B switch) run the
+        torch modules: ~150 launch-bound library ops, captured once per (shape, parameter version) into a CUDA graph and
+        replayed (RTFS_NO_VIDEO_GRAPH=1: eagerly)."""
         rm = self.model.refinement_module
+        P = self.params(mouth.device)
+        Tv = mouth.shape[-1]
+        if P.tensors.get("RTFS_P_VIDEO_PACK") is not None and 8 <= Tv <= 100 and not os.environ.get("RTFS_TORCH_VIDEO"):
+            # the VP block as one kernel (csrc/video.cuh); the video bottleneck of the RTFS-Net configurations is the identity
+            x = self.model.video_bottleneck(mouth).contiguous()
+            out = torch.empty_like(x)
+            _lib.check(_lib.lib().rtfs_video_forward(P.ptr, x.data_ptr(), out.data_ptr(), x.shape[0], Tv, self._stream()), "rtfs_video_forward")
+            return out
         if os.environ.get("RTFS_NO_VIDEO_GRAPH") or torch.cuda.is_current_stream_capturing():
             # (a forward that is itself being captured into a CUDA graph records the eager ops directly)
             return rm.video_net.get_block(0)(self.model.video_bottleneck(mouth)).contiguous()

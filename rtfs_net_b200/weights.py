@@ -74,8 +74,91 @@ TRAIN_ONLY = ("RTFS_P_BN_WT", "RTFS_P_PJ_WT", "RTFS_P_RC_WT", "RTFS_P_MK_WT", "R
 # slots that are images / transposes of another slot: the backward returns no gradient for them (the base slot carries it)
 DERIVED = TRAIN_ONLY[:-1] + ("RTFS_P_BN_WI", "RTFS_P_PJ_WI", "RTFS_P_RC_WI", "RTFS_P_MK_WI", "RTFS_P_RF_WI0", "RTFS_P_RF_WI1", "RTFS_P_RF_WI2",
                              "RTFS_P_RF_WI3", "RTFS_P_RF_CTWI", "RTFS_P_RT_WI0", "RTFS_P_RT_WI1", "RTFS_P_RT_WI2", "RTFS_P_RT_WI3", "RTFS_P_RT_CTWI",
-                             "RTFS_P_RF_FUSED", "RTFS_P_RT_FUSED", "RTFS_P_ENC_WI3", "RTFS_P_AT_WQKVI", "RTFS_P_AT_WOI", "RTFS_P_DEC_W", "RTFS_P_DEC_WT",
+                             "RTFS_P_RF_FUSED", "RTFS_P_RT_FUSED", "RTFS_P_ENC_WI3", "RTFS_P_AT_WQKVI", "RTFS_P_AT_WOI", "RTFS_P_DEC_W", "RTFS_P_DEC_WT", "RTFS_P_VIDEO_PACK",
                              "RTFS_P_WINDOW", "RTFS_P_COSTAB", "RTFS_P_SINTAB", "RTFS_P_CAF_SK", "RTFS_P_CAF_TK", "RTFS_P_CAF_SV", "RTFS_P_CAF_TV")
+
+
+VID = "refinement_module.video_net.blocks."
+
+
+def video_pack_supported(sd):
+    """The VP-block kernel (csrc/video.cuh) is built for the RTFS-Net video configuration: 512 -> 64 channels, four k=3 scales,
+    BatchNorm1d, GlobalAttention with 8 heads and a 128-channel FFN."""
+    try:
+        return (tuple(sd[VID + "projection.full_layer.2.weight"].shape) == (64, 512, 1)
+                and tuple(sd[VID + "downsample_layers.3.full_layer.2.weight"].shape) == (64, 1, 3)
+                and (VID + "downsample_layers.4.full_layer.2.weight") not in sd
+                and (VID + "downsample_layers.0.full_layer.3.running_mean") in sd
+                and tuple(sd[VID + "globalatt.0.MHSA.attention.in_proj_weight"].shape) == (192, 64)
+                and tuple(sd[VID + "globalatt.0.FFN.encoder.full_layer.2.weight"].shape) == (128, 64, 1)
+                and tuple(sd[VID + "globalatt.0.FFN.refiner.full_layer.2.weight"].shape) == (128, 1, 3)
+                and (VID + "globalatt.1.MHSA.norm1.weight") not in sd)
+    except KeyError:
+        return False
+
+
+def pack_video(sd, device, n_head=8):
+    """All parameters of the VP block in the layout of csrc/video.cuh (enum vp_field): transposed 1x1-conv weights, tap-major
+    depthwise filters, eval BatchNorm1d (and the conv bias in front of it) folded into per-channel scale / shift."""
+    g = lambda k: sd[VID + k].detach().to(device=device, dtype=torch.float32)
+    has = lambda k: (VID + k) in sd
+    offs, total = _lib.video_pack_plan()
+    buf = torch.zeros(total, device=device, dtype=torch.float32)
+
+    def put(field, t, at=0):
+        t = t.reshape(-1)
+        buf[offs[field] + at: offs[field] + at + t.numel()] = t
+
+    def bn_fold(q, conv_bias=None):
+        s = g(q + "weight") / torch.sqrt(g(q + "running_var") + 1e-5)
+        b = conv_bias if conv_bias is not None else 0.0
+        return s, (b - g(q + "running_mean")) * s + g(q + "bias")
+
+    put("GW_W", g("gateway.full_layer.2.weight"))
+    put("GW_B", g("gateway.full_layer.2.bias"))
+    put("GW_A", g("gateway.full_layer.4.weight"))
+    put("PJ_WT", g("projection.full_layer.2.weight").reshape(64, 512).t().contiguous())
+    s, t = bn_fold("projection.full_layer.3.", g("projection.full_layer.2.bias"))
+    put("PJ_S", s)
+    put("PJ_T", t)
+    put("PJ_A", g("projection.full_layer.4.weight"))
+    for i in range(4):
+        q = f"downsample_layers.{i}.full_layer."
+        put("DS_W", g(q + "2.weight").reshape(64, 3).t().contiguous(), i * 192)
+        s, t = bn_fold(q + "3.", g(q + "2.bias"))
+        put("DS_S", s, i * 64)
+        put("DS_T", t, i * 64)
+    a = "globalatt.0.MHSA."
+    put("LN1_G", g(a + "norm1.weight"))
+    put("LN1_B", g(a + "norm1.bias"))
+    if has(a + "pos_enc.pe"):
+        put("PE", g(a + "pos_enc.pe")[0, :16])
+    put("IN_WT", g(a + "attention.in_proj_weight").t().contiguous())
+    put("IN_B", g(a + "attention.in_proj_bias"))
+    put("OUT_WT", g(a + "attention.out_proj.weight").t().contiguous())
+    put("OUT_B", g(a + "attention.out_proj.bias"))
+    put("LN2_G", g(a + "norm2.weight"))
+    put("LN2_B", g(a + "norm2.bias"))
+    f = "globalatt.0.FFN."
+    put("F1_WT", g(f + "encoder.full_layer.2.weight").reshape(128, 64).t().contiguous())
+    put("F1_G", g(f + "encoder.full_layer.3.norm.weight"))
+    put("F1_B", g(f + "encoder.full_layer.3.norm.bias"))
+    put("FR_W", g(f + "refiner.full_layer.2.weight").reshape(128, 3).t().contiguous())
+    put("FR_B", g(f + "refiner.full_layer.2.bias"))
+    put("F2_WT", g(f + "decoder.full_layer.2.weight").reshape(64, 128).t().contiguous())
+    put("F2_G", g(f + "decoder.full_layer.3.norm.weight"))
+    put("F2_B", g(f + "decoder.full_layer.3.norm.bias"))
+    units = [f"fusion_layers.{i}." for i in range(4)] + [f"concat_layers.{i}." for i in range(3)]
+    for u, key in enumerate(units):
+        for j, sub in enumerate(("local_embedding.", "global_embedding.", "global_gate.")):
+            q = key + sub + "full_layer."
+            put("TF", g(q + "2.weight").reshape(64, 3).t().contiguous(), u * 960 + j * 320)
+            s, t = bn_fold(q + "3.")
+            put("TF", s, u * 960 + j * 320 + 192)
+            put("TF", t, u * 960 + j * 320 + 256)
+    put("RC_WT", g("residual_conv.full_layer.2.weight").reshape(512, 64).t().contiguous())
+    put("RC_B", g("residual_conv.full_layer.2.bias"))
+    return buf
 
 
 def prepare(sd, device, train=False):
@@ -227,7 +310,9 @@ def prepare(sd, device, train=False):
         out[f"RTFS_P_{tag}_FUSED"] = dprnn_fused_image(
             out[f"RTFS_P_{tag}_W0"], [out[f"RTFS_P_{tag}_W{l}"] for l in (1, 2, 3)], out[f"RTFS_P_{tag}_CTW"])
 
-    missing = [n for n in _lib.PARAM_NAMES if n not in out and not (n in TRAIN_ONLY and not train)]
+    if not train and video_pack_supported(sd):
+        out["RTFS_P_VIDEO_PACK"] = pack_video(sd, device)
+    missing = [n for n in _lib.PARAM_NAMES if n not in out and not (n in TRAIN_ONLY and not train) and n != "RTFS_P_VIDEO_PACK"]
     if missing:
         raise RuntimeError(f"unprepared parameter slots: {missing}")
     return {n: (out[n].contiguous() if n in out else None) for n in _lib.PARAM_NAMES}

@@ -496,3 +496,18 @@ def test_trained_like_weight_scales(golden_sd, O):
     d = float((_sisdr_db(O, out, wav[:, None, :]) - _sisdr_db(O, ref, wav[:, None, :])).abs().max())
     report(f"forward[trained-like scales] waveform rel_l2={e:.3e} |dSI-SDR|={d:.2e} dB")
     assert e <= 1e-3 and d <= 0.01
+
+
+@pytest.mark.parametrize("Tv", [50, 100, 25, 37, 8])
+def test_video_block_kernel(model, golden_sd, O, Tv):
+    """The VP block as one kernel (csrc/video.cuh, fp32 FMAs) against the CPU oracle, and against the torch-module path it replaces."""
+    g = torch.Generator().manual_seed(59 + Tv)
+    v = torch.rand(3, 512, Tv, generator=g)
+    with torch.no_grad():
+        ref = O.video_block(golden_sd, "refinement_module.video_net.blocks.", v)
+        out = model._runtime.video_block(v.cuda())
+        torch_path = model.refinement_module.video_net.get_block(0)(v.cuda())
+    e = rel_l2(out, ref)
+    report(f"video block kernel Tv={Tv} rel_l2={e:.3e} (torch modules on the GPU: {rel_l2(torch_path, ref):.3e})")
+    assert out.shape == ref.shape
+    assert e < TOL_FP32
