@@ -222,6 +222,13 @@ int rtfs_video_pack_plan(int* offsets, int* n_fields);
  * repeats = audio_params.repeats (4 / 6 / 12). */
 int rtfs_avnet_forward(const float* const* params, const float* wav, const float* video, float* out, void* ws, int B, int L, int Tv, int repeats, void* stream);
 
+/* The same forward from the raw lip embedding: mouth (B,512,Tv) -> VP block (rtfs_video_forward) -> video (B,512,Tv, caller's
+ * buffer) -> the rest of rtfs_avnet_forward.  With a second stream the VP block and the CAF video branch (which depend on the
+ * lip embedding only and fill 32 of 148 SMs) run on side_stream next to the first RTFS block pass (event fork / join, graph
+ * capturable); side_stream = NULL runs everything on `stream`.  8 <= Tv <= 100. */
+int rtfs_avnet_forward_av(const float* const* params, const float* wav, const float* mouth, float* video, float* out, void* ws, int B, int L,
+                          int Tv, int repeats, void* stream, void* side_stream);
+
 /* ---- training step (BASELINE configs[2]; reference call chain src/system/core.py:94-117 -> AVNet.forward -> loss.backward(),
  * train.py:135-146).  The forward keeps a tape, the backward consumes it.
  *

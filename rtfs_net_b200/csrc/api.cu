@@ -8,6 +8,7 @@
 #include "../../include/rtfs_b200.h"
 #include "attention.cuh"
 #include "att_tc.cuh"
+#include "att_core_tc.cuh"
 #include "caf.cuh"
 #include "dprnn.cuh"
 #include "dprnn_fused.cuh"
@@ -170,6 +171,13 @@ struct Ctx {
     char* ws;
     cudaStream_t st;
     bool train = false;  // training forward: the dual-path RNNs run the taped kernel chain (train_api.cuh)
+    // rtfs_avnet_forward_av: the VP block + the CAF video branch run on a side stream behind the first block pass's
+    // gateway/projection launch (fork) and are joined in front of the fused CAF epilogue
+    mutable bool fork_armed = false, join_pending = false;
+    cudaStream_t side = nullptr;
+    const float* mouth = nullptr;
+    float* video = nullptr;
+    mutable cudaEvent_t ev_join = nullptr;
     float* buf(int i) const { return reinterpret_cast<float*>(ws + pl.off[i]); }
     double* stat(int slot) const { return reinterpret_cast<double*>(ws + pl.off[RTFS_WS_STATS]) + (long long)slot * d.B * 2; }
     GlnRef gln(int slot, int pg, int pb, long long n) const {
@@ -463,7 +471,16 @@ int run_mhsa(const Ctx& c, const float* g_in, float* g_out) {
         rowblock_ln_kernel<96, 0><<<d.B * d.Tc, 128, smem, c.st>>>(ra);
         CK(cudaGetLastError());
     }
-    {
+    // attention core: tcgen05 + tensor-map TMA (att_core_tc.cuh) up to 256 frames; RTFS_LEGACY_ATTCORE=1 (A/B switch) and longer
+    // sequences run the mma.sync kernel
+    static const bool legacy_core = env_flag("RTFS_LEGACY_ATTCORE");
+    bool core_done = false;
+    if (att_tc && !legacy_core && d.Tc <= 256) {
+        STAGE(RTFS_SG_ATT_CORE);
+        CK(launch_attn_core_tc(ra.q, ra.k, ra.v, c.buf(RTFS_WS_AO), d.B, H, d.Tc, c.st));
+        core_done = true;
+    }
+    if (!core_done) {
         AttnArgs aa;
         aa.q = ra.q;
         aa.k = ra.k;
@@ -528,6 +545,8 @@ int run_mhsa(const Ctx& c, const float* g_in, float* g_out) {
 
 // caf_fused: apply the CAF fusion (vk/att already produced by caf_video_kernel) to the block output in the
 // residual-conv epilogue; addend is then added after the fusion (refinement_module.py:50-56).
+int fork_video(const Ctx& c);
+
 int run_block(const Ctx& c, const float* x, const float* addend, float* out, bool caf_fused = false) {
     const Dims& d = c.d;
     const float* const* P = c.P;
@@ -554,6 +573,7 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out, boo
             CK((launch_gemm<64, 256, false>(al, P[RTFS_P_PJ_W], ep, M, 64, c.st)));
         }
     }
+    if (c.fork_armed) RUN(fork_video(c));
     const bool roll = use_roll();
     if (roll) {
         // S2 PReLU(gLN(p)) -> dw4x4 s1 -> d0_pre                              tdanet.py:61-68,113
@@ -712,6 +732,11 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out, boo
         al.Tc = d.Tc;
         al.Fc = d.Fc;
         al.B = d.B;
+        if (c.join_pending) {  // the fused CAF epilogue reads the side stream's key / attention tables
+            CKN(cudaStreamWaitEvent(c.st, c.ev_join, 0));
+            CKN(cudaEventDestroy(c.ev_join));
+            c.join_pending = false;
+        }
         STAGE(caf_fused ? RTFS_SG_RESID_OUT_CAF : RTFS_SG_RESID_OUT);
         if (caf_fused) {
             if (addend != nullptr && addend != x) return fail_msg("block (fused CAF pass): the addend must be the block input itself");
@@ -761,6 +786,57 @@ int run_caf_video(const Ctx& c, const float* video) {
     STAGE(RTFS_SG_CAF_VIDEO);
     caf_video_kernel<<<d.B, 256, smem, c.st>>>(va);
     CK(cudaGetLastError());
+    return 0;
+}
+
+// VP block of the lip embedding as one kernel (video.cuh): x (B,512,Tv) -> out (B,512,Tv)
+int run_video(const float* const* params, const float* x, float* out, int B, int Tv, cudaStream_t st) {
+    if (params == nullptr || params[RTFS_P_VIDEO_PACK] == nullptr) return fail_msg("rtfs_video_forward: packed video parameters missing");
+    if (B < 1 || Tv < 8 || Tv > 100) return fail_msg("rtfs_video_forward: 8 <= Tv <= 100 frames");
+    VideoArgs a;
+    a.x = x;
+    a.w = params[RTFS_P_VIDEO_PACK];
+    a.out = out;
+    a.off = vp_offsets();
+    a.Tv = Tv;
+    int len = Tv, start = 0;
+    for (int i = 0; i < VP_DEPTH; ++i) {
+        a.len[i] = len;
+        a.start[i] = start;
+        start += len;
+        len = (len - 1) / 2 + 1;  // k = 3, stride 2, padding 1
+    }
+    a.sumlen = start;
+    const int smem = vp_smem_floats(Tv, a.sumlen) * 4;
+    if (smem > 227 * 1024) return fail_msg("rtfs_video_forward: shared-memory budget exceeded");
+    static SmemCfg cfg;
+    CKN(ensure_smem(video_block_kernel, smem, cfg));
+    {
+        struct { cudaStream_t st; } c{st};
+        STAGE(RTFS_SG_VIDEO);
+        video_block_kernel<<<B, 256, smem, st>>>(a);
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+// Fork: the VP block and the CAF video branch depend on the lip embedding only.  One CTA per utterance cannot fill the
+// device, so they run on a (high-priority) side stream next to the full-resolution depthwise / dual-path RNN / attention
+// kernels of the first block pass instead of in front of them; ordinary event fork / join, so the forward stays capturable.
+int fork_video(const Ctx& c) {
+    c.fork_armed = false;
+    cudaEvent_t ev_fork = nullptr;
+    CKN(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    CKN(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
+    CKN(cudaEventRecord(ev_fork, c.st));
+    CKN(cudaStreamWaitEvent(c.side, ev_fork, 0));
+    CKN(cudaEventDestroy(ev_fork));
+    RUN(run_video(c.P, c.mouth, c.video, c.d.B, c.d.Tv, c.side));
+    Ctx cs = c;
+    cs.st = c.side;
+    RUN(run_caf_video(cs, c.video));
+    CKN(cudaEventRecord(c.ev_join, c.side));
+    c.join_pending = true;
     return 0;
 }
 
@@ -927,48 +1003,35 @@ int rtfs_video_pack_plan(int* offsets, int* n_fields) {
 }
 
 int rtfs_video_forward(const float* const* params, const float* x, float* out, int B, int Tv, void* stream) {
-    if (params == nullptr || params[RTFS_P_VIDEO_PACK] == nullptr) return fail_msg("rtfs_video_forward: packed video parameters missing");
-    if (B < 1 || Tv < 8 || Tv > 100) return fail_msg("rtfs_video_forward: 8 <= Tv <= 100 frames");
-    VideoArgs a;
-    a.x = x;
-    a.w = params[RTFS_P_VIDEO_PACK];
-    a.out = out;
-    a.off = vp_offsets();
-    a.Tv = Tv;
-    int len = Tv, start = 0;
-    for (int i = 0; i < VP_DEPTH; ++i) {
-        a.len[i] = len;
-        a.start[i] = start;
-        start += len;
-        len = (len - 1) / 2 + 1;  // k = 3, stride 2, padding 1
-    }
-    a.sumlen = start;
-    const int smem = vp_smem_floats(Tv, a.sumlen) * 4;
-    if (smem > 227 * 1024) return fail_msg("rtfs_video_forward: shared-memory budget exceeded");
-    static SmemCfg cfg;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CKN(ensure_smem(video_block_kernel, smem, cfg));
-    {
-        struct { cudaStream_t st; } c{st};
-        STAGE(RTFS_SG_VIDEO);
-        video_block_kernel<<<B, 256, smem, st>>>(a);
-        CK(cudaGetLastError());
-    }
-    return 0;
+    return run_video(params, x, out, B, Tv, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int rtfs_avnet_forward(const float* const* params, const float* wav, const float* video, float* out, void* ws, int B, int L, int Tv, int repeats, void* stream) {
+static int avnet_forward_impl(const float* const* params, const float* wav, const float* mouth, float* video, float* out, void* ws, int B, int L,
+                              int Tv, int repeats, void* stream, void* side_stream) {
     Ctx c;
     if (!make_ctx(c, params, ws, B, L / 128 + 1, Tv, stream)) return -2;
     if (repeats < 1 || Tv < 1) return fail_msg("rtfs_avnet_forward: repeats < 1 or Tv < 1");
     g_launches = 0;
     float *a0 = c.buf(RTFS_WS_A0), *a1 = c.buf(RTFS_WS_A1), *xa = c.buf(RTFS_WS_XA), *xb = c.buf(RTFS_WS_XB);
+    const bool fused_caf = use_tc() && !env_flag("RTFS_UNFUSED_CAF") && c.d.F >= 32;  // the fused epilogue assumes <= 2 frames per 32 rows
+    bool forked = false;
+    if (mouth != nullptr) {
+        // per-stage timing (rtfs_profile_enable) keeps everything on one stream so that stage times add up
+        if (side_stream != nullptr && side_stream != stream && fused_caf && !g_prof.on) {
+            c.fork_armed = forked = true;
+            c.side = reinterpret_cast<cudaStream_t>(side_stream);
+            c.mouth = mouth;
+            c.video = video;
+        } else {
+            RUN(run_video(params, mouth, video, B, Tv, c.st));
+        }
+    }
     RUN(run_encoder(c, wav, a0, L));
     RUN(run_bottleneck(c, a0, a1, false));
     // refinement_module.py:45-62 with fusion_repeats = 1
     float *cur = xb, *other = xa;
-    if (use_tc() && !env_flag("RTFS_UNFUSED_CAF") && c.d.F >= 32) {  // the fused epilogue assumes <= 2 frames per 32 rows
-        RUN(run_caf_video(c, video));
+    if (fused_caf) {
+        if (!forked) RUN(run_caf_video(c, video));
         RUN(run_block(c, a1, repeats > 1 ? a1 : nullptr, xb, true));
     } else {
         RUN(run_block(c, a1, nullptr, xa));
@@ -989,6 +1052,16 @@ int rtfs_avnet_forward(const float* const* params, const float* wav, const float
         RUN(run_decoder(c, a1, out, L));
     }
     return 0;
+}
+
+int rtfs_avnet_forward(const float* const* params, const float* wav, const float* video, float* out, void* ws, int B, int L, int Tv, int repeats, void* stream) {
+    return avnet_forward_impl(params, wav, nullptr, const_cast<float*>(video), out, ws, B, L, Tv, repeats, stream, nullptr);
+}
+
+int rtfs_avnet_forward_av(const float* const* params, const float* wav, const float* mouth, float* video, float* out, void* ws, int B, int L, int Tv,
+                          int repeats, void* stream, void* side_stream) {
+    if (mouth == nullptr || video == nullptr) return fail_msg("rtfs_avnet_forward_av: mouth / video buffer missing");
+    return avnet_forward_impl(params, wav, mouth, video, out, ws, B, L, Tv, repeats, stream, side_stream);
 }
 
 }  // extern "C"

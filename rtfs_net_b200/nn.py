@@ -581,6 +581,7 @@ class _Runtime:
         self._ws_key = None
         self._vgraph = {}  # (device, shape, parameter key) -> (CUDAGraph, static input, static output) of the video block
         self._train_bufs = None
+        self._side_streams = {}  # device index -> high-priority stream of the forked VP block
 
     # ---------------------------------------------------------------- plumbing
     def _needs_train_path(self):
@@ -748,6 +749,18 @@ class _Runtime:
         return out.view(B, -1, L)
 
     # ---------------------------------------------------------------- video (VP) block
+    @staticmethod
+    def _video_kernel_ok(P, Tv):
+        return P.tensors.get("RTFS_P_VIDEO_PACK") is not None and 8 <= Tv <= 100 and not os.environ.get("RTFS_TORCH_VIDEO")
+
+    def _side_stream(self, device):
+        """One high-priority stream per device for the forked VP block (joined before the forward returns)."""
+        key = torch.device(device).index
+        st = self._side_streams.get(key)
+        if st is None:
+            st = self._side_streams[key] = torch.cuda.Stream(device=device, priority=-1)
+        return st
+
     def video_block(self, mouth):
         """The VP block (tdanet.py:106-133 in 1-D, attention.py:9-73,192-220): one hand-written kernel per call (csrc/video.cuh)
         for the RTFS-Net video configuration and 8..100 frames.  Other shapes (and RTFS_TORCH_VIDEO=1, the A/B switch) run the
@@ -756,7 +769,7 @@ class _Runtime:
         rm = self.model.refinement_module
         P = self.params(mouth.device)
         Tv = mouth.shape[-1]
-        if P.tensors.get("RTFS_P_VIDEO_PACK") is not None and 8 <= Tv <= 100 and not os.environ.get("RTFS_TORCH_VIDEO"):
+        if self._video_kernel_ok(P, Tv):
             # the VP block as one kernel (csrc/video.cuh); the video bottleneck of the RTFS-Net configurations is the identity
             x = self.model.video_bottleneck(mouth).contiguous()
             out = torch.empty_like(x)
@@ -827,12 +840,22 @@ class _Runtime:
         R = rm.audio_params["repeats"]
         with torch.cuda.device(wav.device):
             P = self.params(wav.device)
-            video = self.video_block(mouth.contiguous())
-            Tv = video.shape[-1]
-            ws = self.workspace(B, L, Tv, wav.device)
+            Tv = mouth.shape[-1]
             out = torch.empty(B, L, device=wav.device, dtype=torch.float32)
-            _lib.check(_lib.lib().rtfs_avnet_forward(P.ptr, wav.data_ptr(), video.data_ptr(), out.data_ptr(), ws.data_ptr(), B, L, Tv, R, self._stream()),
-                       "rtfs_avnet_forward")
+            if self._video_kernel_ok(P, Tv):
+                # one C call from the raw lip embedding; the VP block + the CAF video branch run on a high-priority side stream
+                # next to the first block pass (RTFS_NO_VIDEO_FORK=1, the A/B switch: everything on the current stream)
+                x = self.model.video_bottleneck(mouth).contiguous()
+                video = torch.empty_like(x)
+                ws = self.workspace(B, L, Tv, wav.device)
+                side = 0 if os.environ.get("RTFS_NO_VIDEO_FORK") else self._side_stream(wav.device).cuda_stream
+                _lib.check(_lib.lib().rtfs_avnet_forward_av(P.ptr, wav.data_ptr(), x.data_ptr(), video.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                                            B, L, Tv, R, self._stream(), side), "rtfs_avnet_forward_av")
+            else:
+                video = self.video_block(mouth.contiguous())
+                ws = self.workspace(B, L, Tv, wav.device)
+                _lib.check(_lib.lib().rtfs_avnet_forward(P.ptr, wav.data_ptr(), video.data_ptr(), out.data_ptr(), ws.data_ptr(), B, L, Tv, R, self._stream()),
+                           "rtfs_avnet_forward")
         return out.view(B, 1, L)
 
 
