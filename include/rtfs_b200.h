@@ -211,6 +211,18 @@ int rtfs_mask_forward(const float* const* params, const float* refined, const fl
 /* STFTDecoder.forward (TDAVNet/decoder.py:110-132): z (B,T,F,256) -> wav (B,L). */
 int rtfs_decoder_forward(const float* const* params, const float* z, float* wav_out, void* ws, int B, int L, void* stream);
 
+/* ---- input pipeline on the device (reference: the per-utterance numpy work of the DataLoader workers).
+ * Lip-ROI transforms of get_preprocessing_pipelines() (src/datas/transform.py:151-167): Normalize(0,255) -> CenterCrop /
+ * RandomCrop(crop) -> HorizontalFlip -> Normalize(mean, std).  roi (B,T,H,W) uint8 -> out (B,1,T,crop,crop) fp32.
+ * off_y / off_x / flip: per-utterance crop offsets and flip decisions drawn by the host (NULL = centre crop / no flip,
+ * transform.py:86-102); crop % 4 == 0. */
+int rtfs_mouth_preprocess(const unsigned char* roi, float* out, const int* off_y, const int* off_x, const int* flip, int B, int T, int H, int W,
+                          int crop, float mean, float std, void* stream);
+/* normalize_tensor_wav as AVSpeechDataset.__getitem__ applies it (src/datas/avspeech_dataset.py:10-14,128-131,167-170):
+ * mix (B,L) -> (x - mean) / (std + eps) with the unbiased std of the mixture; src (B,n_src,L) -> (s - mean_s) / (std_mix + eps).
+ * n_src = 0: mixture only (src / src_out may be NULL). */
+int rtfs_wav_normalize(const float* mix, const float* src, float* mix_out, float* src_out, int B, int L, int n_src, float eps, void* stream);
+
 /* TDANetBlock.forward with is2d = False (separators/tdanet.py:106-133; GlobalAttention layers/attention.py:28-73,192-220): the VP
  * block on the lip embedding, x (B,512,Tv) -> out (B,512,Tv), one kernel, inference (eval BatchNorm).  8 <= Tv <= 100. */
 int rtfs_video_forward(const float* const* params, const float* x, float* out, int B, int Tv, void* stream);

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("RTFS_B200_LIB", os.path.join(HERE, "lib", "librtfs_b2
 _c_p = ctypes.c_void_p
 _c_i = ctypes.c_int
 _c_ll = ctypes.c_longlong
+_c_f = ctypes.c_float
 
 # name -> (restype, argtypes); must list every function include/rtfs_b200.h declares
 PROTOTYPES = {
@@ -35,6 +36,8 @@ PROTOTYPES = {
     "rtfs_avnet_forward": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_p]),
     "rtfs_avnet_forward_av": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_p, _c_p]),
     "rtfs_video_forward": (_c_i, [_c_p, _c_p, _c_p, _c_i, _c_i, _c_p]),
+    "rtfs_mouth_preprocess": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_f, _c_f, _c_p]),
+    "rtfs_wav_normalize": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_f, _c_p]),
     "rtfs_video_pack_plan": (_c_i, [ctypes.POINTER(_c_i), ctypes.POINTER(_c_i)]),
     # training step
     "rtfs_train_plan": (_c_ll, [_c_i, _c_i, _c_i, _c_i, ctypes.POINTER(_c_ll), ctypes.POINTER(_c_ll), ctypes.POINTER(_c_ll), ctypes.POINTER(_c_ll)]),

@@ -18,6 +18,7 @@
 #include "gemm.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tcp.cuh"
+#include "input.cuh"
 #include "video.cuh"
 
 using namespace rtfs;
@@ -1000,6 +1001,31 @@ int rtfs_video_pack_plan(int* offsets, int* n_fields) {
         for (int i = 0; i < VP_COUNT; ++i) offsets[i] = o.o[i];
     if (n_fields) *n_fields = VP_COUNT;
     return o.total;
+}
+
+int rtfs_mouth_preprocess(const unsigned char* roi, float* out, const int* off_y, const int* off_x, const int* flip, int B, int T, int H, int W, int crop,
+                          float mean, float std, void* stream) {
+    if (roi == nullptr || out == nullptr) return fail_msg("rtfs_mouth_preprocess: null buffer");
+    if (B < 1 || T < 1 || crop < 4 || (crop & 3) || crop > H || crop > W) return fail_msg("rtfs_mouth_preprocess: crop must be a multiple of 4 inside the ROI");
+    if ((off_y == nullptr) != (off_x == nullptr)) return fail_msg("rtfs_mouth_preprocess: off_y and off_x go together");
+    if (!(std > 0.f)) return fail_msg("rtfs_mouth_preprocess: std must be positive");
+    MouthPrepArgs a{roi, out, off_y, off_x, flip, B, T, H, W, crop, mean, std};
+    const long long total = (long long)B * T * crop * (crop / 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+    mouth_preprocess_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int rtfs_wav_normalize(const float* mix, const float* src, float* mix_out, float* src_out, int B, int L, int n_src, float eps, void* stream) {
+    if (mix == nullptr || mix_out == nullptr) return fail_msg("rtfs_wav_normalize: null mixture buffer");
+    if (n_src > 0 && (src == nullptr || src_out == nullptr)) return fail_msg("rtfs_wav_normalize: null source buffer");
+    if (B < 1 || L < 2 || n_src < 0) return fail_msg("rtfs_wav_normalize: B >= 1, L >= 2, n_src >= 0");
+    WavNormArgs a{mix, src, mix_out, src_out, B, L, n_src, eps};
+    wav_normalize_kernel<<<dim3(1 + n_src, B), 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    CK(cudaGetLastError());
+    return 0;
 }
 
 int rtfs_video_forward(const float* const* params, const float* x, float* out, int B, int Tv, void* stream) {
