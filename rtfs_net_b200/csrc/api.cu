@@ -316,9 +316,8 @@ int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_f
         a.L = L;
         a.nseq_total = nseq;
         a.n_other = n_other;
-        a.nseq_tile = DF_NP / S < 4 ? DF_NP / S : 4;
         static const bool dbg = env_flag("RTFS_DF_DEBUG");
-        const int tiles = (a.nseq_total + a.nseq_tile - 1) / a.nseq_tile;
+        const int tiles = dprnn_fused_dbg_rows(S, nseq);  // timeline rows; nseq_tile is set by the launcher for the tile size it picks
         if (dbg) {
             CKN(cudaMalloc(&a.dbg, sizeof(long long) * 32 * tiles));
             CKN(cudaMemset(a.dbg, 0, sizeof(long long) * 32 * tiles));
@@ -331,9 +330,9 @@ int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_f
             std::vector<long long> h(32 * (size_t)tiles);
             CKN(cudaMemcpy(h.data(), a.dbg, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
             cudaFree(a.dbg);
-            const int picks[3] = {0, tiles / 2, tiles - 1};
+            const int picks[3] = {0, 1, tiles - 1};
             for (int t : picks) {
-                fprintf(stderr, "dprnn_fused which=%d tile %d/%d:", which, t, tiles);
+                fprintf(stderr, "dprnn_fused which=%d row %d/%d (start %+lld):", which, t, tiles, h[16 * t] - h[0]);
                 for (int i = 1; i < 16 && h[16 * t + i] != 0; ++i) fprintf(stderr, " %lld", h[16 * t + i] - h[16 * t + i - 1]);
                 fprintf(stderr, " | h-warp spans:");
                 for (int i = 0; i < 4; ++i) fprintf(stderr, " %lld", h[16 * (tiles + t) + 2 * i + 1] - h[16 * (tiles + t) + 2 * i]);
