@@ -317,7 +317,8 @@ int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_f
         a.nseq_total = nseq;
         a.n_other = n_other;
         static const bool dbg = env_flag("RTFS_DF_DEBUG");
-        const int tiles = dprnn_fused_dbg_rows(S, nseq);  // timeline rows; nseq_tile is set by the launcher for the tile size it picks
+        a.yield_sms = c.join_pending ? 1 : 0;  // the forked VP block needs SMs: no persistent CTAs while it is in flight
+        const int tiles = dprnn_fused_dbg_rows(S, nseq, c.join_pending);  // timeline rows; nseq_tile is set by the launcher for the tile size it picks
         if (dbg) {
             CKN(cudaMalloc(&a.dbg, sizeof(long long) * 32 * tiles));
             CKN(cudaMemset(a.dbg, 0, sizeof(long long) * 32 * tiles));

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(192, 1) attn_core_tc_kernel(const __grid_const
 
     if (warp == 4) {
         // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             tma_prefetch_desc(&mq);
             tma_prefetch_desc(&mk);
             tma_prefetch_desc(&mv);
@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(192, 1) attn_core_tc_kernel(const __grid_const
                 }
         }
     } else if (warp == 5) {
-        // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // ------------------------------------------------------------ MMA issuer (uniform-register issue: gemm_tc.cuh elect_one)
+        if (elect_one()) {
             constexpr uint32_t IDESC_S = umma_idesc_tf32(128, KP);
             constexpr uint32_t IDESC_O = umma_idesc_tf32_bmn(128, 256);
             for (int c = 0; c < 8; ++c) {

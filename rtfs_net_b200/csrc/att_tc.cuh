@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128, ac_ctas<MODE>()) att_conv_ln_tc_kernel(At
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {  // issued straight from uniform registers (gemm_tc.cuh: elect_one)
             if (it == 0) mbar_wait(w_ready, 0);
             const uint32_t ab = smem_u32(a_slab), wb = smem_u32(w_slab);
 #pragma unroll

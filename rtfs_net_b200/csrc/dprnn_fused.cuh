@@ -27,7 +27,7 @@
 namespace rtfs {
 
 constexpr int DF_NP = 256;                 // largest tile (positions); sequences longer than this take the unfused path
-constexpr int DF_NSTG = 5;
+constexpr int DF_NSTG = 4;                 // regular weight-ring slots (and units a producer may run ahead of a phase)
 constexpr int DF_SLAB = 16384;             // one weight slab of the image (weights.py: dprnn_fused_image)
 constexpr int DF_NSLAB = 32 + 3 * 4 + 8;   // layer 0 | layers 1-3 | transposed conv
 
@@ -48,7 +48,33 @@ struct DfC {
     static constexpr int NUNIT = DF_NSLAB * UPS;
     static constexpr int SMEM = HBUF + CS + DF_NSTG * WCH + 2 * NP * 4 + 256 + 8 * 16 * 8;  // one pipeline
     static constexpr int MINB = NP == 256 ? 1 : 2;
+    // Weight ring.  A bulk copy lands ~1000 cycles after it is issued, so a 4-unit ring sustains ~30 B/clk -- half of what the
+    // layer-0 GEMM (512 KB of weights per tile) consumes at the tensor rate.  The c buffer (= 4 units, directly below the ring) is idle
+    // until the first recurrence, so layer 0 cycles through 8 slots (c buffer + ring), the later layers through the ring's 4.
+    static constexpr int NSLOT = 8;
+    static constexpr int L0U = 32 * UPS;  // layer-0 units per tile
+    static_assert(CS == 4 * WCH, "the c buffer holds exactly four ring units");
+    // every slot sees an even number of uses per tile (or the CTA runs one tile), so barrier parities do not depend on the tile
+    static_assert(NP == 256 || ((L0U / 8) % 2 == 0 && ((NUNIT - L0U) / 4) % 2 == 0), "ring parities must repeat per tile");
+    static_assert(L0U % 8 == 0 && (NUNIT - L0U) % 4 == 0 && NUNIT % 4 == 0, "units fill the slots evenly");
 };
+constexpr int DF_NPROD = 4;
+// Slot (0-3: c buffer, 4-7: ring; also the index of its barriers) and wait parity of weight unit u of a tile.  Layer 0 starts on the
+// ring slots (its first units are fetched while the previous tile's epilogue still stages through the c buffer).  Producer p
+// (warp p + 1 of the pipeline) fetches the units u = p mod 4, which are exactly the uses of slots p and p + 4: every slot is
+// refilled by ONE thread, in order -- a parity wait is only sound while the waiter is at most one phase behind.
+template <int NP>
+DEVINL void df_unit_slot(int u, int& slot, uint32_t& par) {
+    using C = DfC<NP>;
+    if (u < C::L0U) {
+        slot = (u + 4) & 7;
+        par = (uint32_t)(u >> 3) & 1u;
+    } else {
+        const int v = u - C::L0U;
+        slot = 4 + (v & 3);
+        par = (uint32_t)(v >> 2) & 1u;  // L0U / 8 earlier uses: an even number
+    }
+}
 
 struct DfArgs {
     const float* g_in;    // (B,Tc,Fc,64) when first == 0
@@ -68,6 +94,7 @@ struct DfArgs {
     int first;
     int S, L;       // sequence length, SRU steps (S - 7)
     int nseq_total, nseq_tile, n_other;
+    int yield_sms;   // a side-stream kernel is in flight (forked VP block): run one-tile CTAs, which leave SMs as they finish
     long long* dbg;  // optional: [tiles][16] clock64 stamps of thread 0 at the phase boundaries
 };
 
@@ -171,15 +198,7 @@ DEVINL void df_hchunk(uint32_t tl, int m, bool rev, int p_lo, int p_hi, int p_en
     }
 }
 
-// true in exactly one lane of a converged warp; code guarded by it issues tcgen05 / bulk-copy instructions straight from uniform
-// registers (issued from an `if (tid == 0)` branch, every UTCHMMA / UTCBAR is wrapped in an ELECT + 5 x R2UR.BROADCAST + branch
-// loop: measured 102 cycles of issue time per MMA and 120 per commit, against 62 per MMA here -- tools/probe/dfissue_probe.cu)
-DEVINL bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-constexpr int DF_NPROD = 4;  // weight-producer warps: one thread sustains one cp.async.bulk per ~300-500 cycles whatever its size
+// (weight-producer warps: one thread sustains one cp.async.bulk per ~300-500 cycles whatever its size, so DF_NPROD warps share the stream)
 DEVINL void df_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // DUAL = false: one tile per CTA, grid = tiles (NP = 256: one CTA per SM; NP = 128: two).
@@ -202,8 +221,9 @@ __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::
     unsigned char* wring = sm + DF_HBUF + DF_CS;
     int* pos2off = reinterpret_cast<int*>(wring + DF_NSTG * DF_WCH);  // [2][NP]: double-buffered over tiles
     uint64_t* full_w = reinterpret_cast<uint64_t*>(pos2off + 2 * NP);
-    uint64_t* mma_done = full_w + DF_NSTG;
-    uint64_t* acc_ready = mma_done + DF_NSTG;
+    uint64_t* mma_done = full_w + C::NSLOT;
+    uint64_t* acc_ready = mma_done + C::NSLOT;
+    static_assert((2 * C::NSLOT + 1) * 8 + 32 <= 256, "barriers + seqstat fit their 256 bytes");
     float* seqstat = reinterpret_cast<float*>(acc_ready + 1);  // [4 sequences][mean, rstd] of the gLN applied when first
     // chunk_bar[(sequence, direction)][16-step block]: c-recurrence warp -> h warp hand-off, one completion per layer
     uint64_t* chunk_bar = reinterpret_cast<uint64_t*>(sm + DF_HBUF + DF_CS + DF_NSTG * DF_WCH + 2 * NP * 4 + 256);
@@ -232,7 +252,7 @@ __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::
     // barrier initialisation before anything is in flight: its release fence would otherwise wait for the loads below
     if (tid == 32) {
 #pragma unroll
-        for (int s = 0; s < DF_NSTG; ++s) {
+        for (int s = 0; s < C::NSLOT; ++s) {
             mbar_init(full_w + s, 1);
             mbar_init(mma_done + s, 1);
         }
@@ -253,22 +273,24 @@ __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::
     tc_fence_after();
     const uint32_t tmem = *tmem_slot + (uint32_t)(half * 2 * NP);
 
-    // ---- weight producers (warps 1..DF_NPROD of the pipeline, every DF_NPROD-th unit each): ring unit G -> slot G % 5, image unit
-    //      G % NUNIT; G runs over all tiles.  Called by the whole warp, one lane issues.
+    // ---- weight producers (warps 1..DF_NPROD of the pipeline): unit G (counted over all tiles) -> image unit G % NUNIT, slot and
+    //      parity from df_unit_slot.  Called by the whole warp, one lane issues.
     const int wtotal = niter * C::NUNIT;
     const bool is_prod = warp >= 1 && warp <= DF_NPROD;
-    int wnext = warp - 1;
+    int wnext = warp - 1;  // next unit of this producer, counted over all tiles
     auto produce_until = [&](int limit) {
         if (limit > wtotal) limit = wtotal;
         const bool lead = elect_one();
-        while (wnext < limit) {
+        for (; wnext < limit; wnext += DF_NPROD) {
             if (lead) {
-                const int slot = wnext % DF_NSTG;
-                if (wnext >= DF_NSTG) mbar_wait(mma_done + slot, ((wnext / DF_NSTG) - 1) & 1);
+                const int u = wnext % C::NUNIT;
+                int slot;
+                uint32_t par;
+                df_unit_slot<NP>(u, slot, par);
+                if (wnext >= C::NSLOT) mbar_wait(mma_done + slot, par ^ 1u);  // the slot's previous use has been multiplied
                 mbar_expect_tx(full_w + slot, DF_WCH);
-                bulk_g2s(wring + slot * DF_WCH, a.wimg + (size_t)(wnext % C::NUNIT) * (DF_WCH / 4), DF_WCH, full_w + slot);
+                bulk_g2s(reinterpret_cast<unsigned char*>(cs) + slot * DF_WCH, a.wimg + (size_t)u * (DF_WCH / 4), DF_WCH, full_w + slot);
             }
-            wnext += DF_NPROD;
         }
         __syncwarp();
     };
@@ -277,8 +299,8 @@ __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::
     const int l16 = tid & 15, c = l16 * 4;
     // descriptors are advanced by integer adds on the (address >> 4) field: one 16-byte slab row = 1, one 4-channel piece = LBO / 16
     const uint64_t d_slab = umma_desc(smem_u32(hbuf), DF_LBO, 128);       // slab rows as the positions operand
-    const uint64_t d_wsru = umma_desc(smem_u32(wring), 2048, 128);       // SRU weights: 128 features x 4-channel pieces
-    const uint64_t d_wct = umma_desc(smem_u32(wring), 1024, 128);        // transposed-conv weights: 64 outputs x 4-channel pieces
+    const uint64_t d_wsru = umma_desc(smem_u32(cs), 2048, 128);          // SRU weights (slot 0): 128 features x 4-channel pieces
+    const uint64_t d_wct = umma_desc(smem_u32(cs), 1024, 128);           // transposed-conv weights: 64 outputs x 4-channel pieces
     constexpr uint32_t PIECE = DF_LBO / 16, UNIT16 = DF_WCH / 16;
     constexpr uint32_t IDESC_SRU = umma_idesc_tf32(128, NP);
     constexpr uint32_t IDESC_CT = umma_idesc_tf32(128, 64);
@@ -412,15 +434,15 @@ __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::
                         if (half == 1) mbar_wait(l0_done, it & 1);
                         else if (it > 0) mbar_wait(l0_done + 1, (it - 1) & 1);
                     }
-                    int g = ubase + cbeg * UPS;
-                    int slot = g % DF_NSTG;
-                    uint32_t par = (uint32_t)(g / DF_NSTG) & 1u;
                     for (int gl = 0; gl < nch; ++gl) {
                         const uint32_t tap = ly == 0 ? (uint32_t)(gl >> 2) : 0u;
                         const uint32_t cb = (uint32_t)(ly == 0 ? (gl & 3) : gl) * 4u;
                         const uint64_t db = d_slab + (uint64_t)(cb * PIECE + 7u + tap);
 #pragma unroll
                         for (int hf = 0; hf < UPS; ++hf) {  // UPS = 2: accumulator 0's 16 K-channels, then accumulator 1's
+                            int slot;
+                            uint32_t par;
+                            df_unit_slot<NP>((cbeg + gl) * UPS + hf, slot, par);
                             mbar_wait(full_w + slot, par);
                             tc_fence_after();
                             const uint64_t da = d_wsru + (uint64_t)((uint32_t)slot * UNIT16);
@@ -435,10 +457,6 @@ __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::
                                 umma_tf32(tmem + hf * NP, da + 256u, db + 2u * PIECE, IDESC_SRU, 1u);
                             }
                             umma_commit(mma_done + slot);
-                            if (++slot == DF_NSTG) {
-                                slot = 0;
-                                par ^= 1u;
-                            }
                         }
                     }
                     if (DUAL && ly == 0) umma_commit(l0_done + half);
@@ -539,12 +557,12 @@ __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::
         // ---- ConvTranspose1d: out[positions][64] = sum_kk slab[p + kk] . Wct_kk   (positions on the lanes)
         if (warp == 0) {
             if (elect_one()) {
-                int g = ubase + cbeg * UPS;
-                int slot = g % DF_NSTG;
-                uint32_t par = (uint32_t)(g / DF_NSTG) & 1u;
                 for (int gl = 0; gl < 8; ++gl) {
 #pragma unroll
                     for (int hf = 0; hf < UPS; ++hf) {  // a unit holds 16 / UPS K-pieces (4 channels each) of tap gl
+                        int slot;
+                        uint32_t par;
+                        df_unit_slot<NP>((cbeg + gl) * UPS + hf, slot, par);
                         mbar_wait(full_w + slot, par);
                         tc_fence_after();
                         const uint64_t dw = d_wct + (uint64_t)((uint32_t)slot * UNIT16);
@@ -557,10 +575,6 @@ __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::
                             if (NP == 256) umma_tf32(tmem + 64, dh + 128u, dw + (uint64_t)(kk * 128), IDESC_CT, acc_on);
                         }
                         umma_commit(mma_done + slot);
-                        if (++slot == DF_NSTG) {
-                            slot = 0;
-                            par ^= 1u;
-                        }
                     }
                 }
                 umma_commit(acc_ready);
@@ -621,26 +635,28 @@ inline cudaError_t launch_dprnn_fused_g(DfArgs a, int tiles, cudaStream_t st) {
 // Tile size: sequences of up to 128 steps run on 128-position tiles, two pipelines per persistent CTA; longer ones on 256-position
 // tiles, one per CTA.  RTFS_DF_TILE=256 forces the latter (the round-1 kernel, kept as the A/B baseline), RTFS_DF_TILE=128 the
 // 128-position tiles as independent CTAs (two resident per SM, no hand-off).
-inline int dprnn_fused_mode(int S) {  // 0: 256-position tiles, 1: 128-position CTAs, 2: two 128-position pipelines per CTA
+// The persistent kernel holds every SM for the whole launch (225 KB of shared memory per CTA), so a kernel forked onto a side stream
+// would wait behind it: while one is in flight (yield_sms) the one-tile CTAs are used instead.
+inline int dprnn_fused_mode(int S, bool yield_sms) {  // 0: 256-position tiles, 1: 128-position CTAs, 2: two 128-position pipelines per CTA
     static const int forced = [] {
         const char* v = getenv("RTFS_DF_TILE");
         return v ? atoi(v) : 0;
     }();
-    if (forced == 256 || S > 128) return 0;
+    if (forced == 256 || S > 128 || (yield_sms && forced == 0)) return 0;
     return forced == 128 ? 1 : 2;
 }
-inline int dprnn_fused_seq_per_tile(int S) {
-    const int np = dprnn_fused_mode(S) == 0 ? 256 : 128, ng = np / 64;
+inline int dprnn_fused_seq_per_tile(int S, bool yield_sms) {
+    const int np = dprnn_fused_mode(S, yield_sms) == 0 ? 256 : 128, ng = np / 64;
     return np / S < ng ? np / S : ng;
 }
-inline int dprnn_fused_tiles(int S, int nseq_total) {
-    const int per = dprnn_fused_seq_per_tile(S);
+inline int dprnn_fused_tiles(int S, int nseq_total, bool yield_sms) {
+    const int per = dprnn_fused_seq_per_tile(S, yield_sms);
     return (nseq_total + per - 1) / per;
 }
 // rows of 16 clock64 stamps the kernel writes when DfArgs::dbg is set (x 2: the h-warp spans of the one-tile-per-CTA kernels)
-inline int dprnn_fused_dbg_rows(int S, int nseq_total) {
-    const int tiles = dprnn_fused_tiles(S, nseq_total);
-    if (dprnn_fused_mode(S) != 2) return tiles;
+inline int dprnn_fused_dbg_rows(int S, int nseq_total, bool yield_sms) {
+    const int tiles = dprnn_fused_tiles(S, nseq_total, yield_sms);
+    if (dprnn_fused_mode(S, yield_sms) != 2) return tiles;
     const int grid = (tiles + 1) / 2 < sm_count() ? (tiles + 1) / 2 : sm_count();
     return 2 * grid;
 }
@@ -649,9 +665,9 @@ inline cudaError_t launch_dprnn_fused(DfArgs a, cudaStream_t st) {
         const char* v = getenv("RTFS_DF_GATE");  // A/B of the gate arithmetic (see df_gate); tanh.approx measured parity-neutral
         return v ? atoi(v) : 1;
     }();
-    const int mode = dprnn_fused_mode(a.S);
-    a.nseq_tile = dprnn_fused_seq_per_tile(a.S);
-    const int tiles = dprnn_fused_tiles(a.S, a.nseq_total);
+    const int mode = dprnn_fused_mode(a.S, a.yield_sms != 0);
+    a.nseq_tile = dprnn_fused_seq_per_tile(a.S, a.yield_sms != 0);
+    const int tiles = dprnn_fused_tiles(a.S, a.nseq_total, a.yield_sms != 0);
     if (mode == 2) {
         if (gate == 1) return launch_dprnn_fused_g<1, 128, true>(a, tiles, st);
         if (gate == 2) return launch_dprnn_fused_g<2, 128, true>(a, tiles, st);

@@ -52,6 +52,21 @@ DEVINL void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) 
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// True in exactly one lane of a CONVERGED warp (all 32 lanes must reach it).  tcgen05 / bulk-copy instructions take their operands
+// from uniform registers: issued from an `if (tid == 0)` branch every UTCHMMA / UTCBAR is wrapped by the compiler in an ELECT +
+// 5 x R2UR.BROADCAST + branch loop (measured 102 cycles of issue time per MMA and 120 per commit); behind elect.sync they are
+// issued straight from uniform registers (62 cycles per MMA: tools/probe/dfissue_probe.cu, profiles/r02_df_probes.txt).
+DEVINL bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// as elect_one, also returning the elected lane (the same value in every lane) so that state it kept can be broadcast afterwards
+DEVINL bool elect_leader(uint32_t& leader) {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync %0|p, 0xffffffff;\n\tselp.u32 %1, 1, 0, p;\n\t}" : "=r"(leader), "=r"(pred));
+    return pred != 0;
+}
 DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 DEVINL void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -688,7 +703,7 @@ __global__ void __launch_bounds__(NT, MINB) gemm_tc_kernel(AL al, const float* _
         mbar_expect_tx(full_w + s, WBYTES);
         bulk_g2s(w_stage + (size_t)s * WBYTES, Wimg + (size_t)c * (BN * TC_KC), WBYTES, full_w + s);
     };
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
 #pragma unroll
         for (int c = 0; c < PD && c < NK; ++c) issue_w(c);
     }
@@ -723,7 +738,7 @@ __global__ void __launch_bounds__(NT, MINB) gemm_tc_kernel(AL al, const float* _
         for (int kc = 0; kc < NK; ++kc) {
             const int s = kc % NS;
             if (kc >= NS) mbar_wait(mma_done + s, ((kc / NS) - 1) & 1);
-            if (NK > NS && tid == 0 && kc + PD < NK) {
+            if (NK > NS && kc + PD < NK && warp == 0 && elect_one()) {
                 const int c = kc + PD;
                 if (c >= NS) mbar_wait(mma_done + (c % NS), ((c / NS) - 1) & 1);
                 issue_w(c);
@@ -743,7 +758,7 @@ __global__ void __launch_bounds__(NT, MINB) gemm_tc_kernel(AL al, const float* _
                 for (int i = 0; i < RPT; ++i) raw[i] = al.raw_load(i, (kc + 1) * TC_KC + kq * 4);
             }
             __syncthreads();
-            if (tid == 0) issue_mma(kc, s);
+            if (warp == 0 && elect_one()) issue_mma(kc, s);
         }
     } else {
     float4 areg[PF][RPT];
@@ -757,7 +772,7 @@ __global__ void __launch_bounds__(NT, MINB) gemm_tc_kernel(AL al, const float* _
     for (int kc = 0; kc < NK; ++kc) {
         const int s = kc % NS;
         if (kc >= NS) mbar_wait(mma_done + s, ((kc / NS) - 1) & 1);  // MMAs of chunk kc-NS have read this stage
-        if (NK > NS && tid == 0 && kc + PD < NK) {
+        if (NK > NS && kc + PD < NK && warp == 0 && elect_one()) {
             const int c = kc + PD;  // its stage was last read by chunk c-NS = kc-2
             if (c >= NS) mbar_wait(mma_done + (c % NS), ((c / NS) - 1) & 1);
             issue_w(c);
@@ -778,7 +793,7 @@ __global__ void __launch_bounds__(NT, MINB) gemm_tc_kernel(AL al, const float* _
             for (int i = 0; i < RPT; ++i) areg[kc % PF][i] = al.load(i, (kc + PF) * TC_KC + kq * 4);
         }
         __syncthreads();
-        if (tid == 0) issue_mma(kc, s);
+        if (warp == 0 && elect_one()) issue_mma(kc, s);
     }
     }
     // accumulator complete once the last chunk's commit has arrived (commits complete in order)
@@ -900,7 +915,7 @@ __global__ void __launch_bounds__(TC_THREADS, MINB) gemm_tc_unfold_kernel(const 
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     constexpr uint32_t IDESC = umma_idesc_tf32(TC_BM, BN);
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
         auto issue_w = [&](int c) {
             const int s = c % NS;
             mbar_expect_tx(full_w + s, WBYTES);

@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
         }
     } else if (warp == MMA_WARP) {
         // ================================================================= MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {
             int it = 0, ga = 0;
 #ifdef RTFS_PROBE_TIMING  // tools/probe/tcp_ablate.cu: cycles the MMA thread waits on each barrier kind
             long long t_te = 0, t_fw = 0, t_fa = 0, t0 = clock64(), tq;
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
         }
     } else {
         // ================================================================= weight loader
-        if (lane == 0) {
+        if (elect_one()) {
             if (WRES) {
                 for (int c = 0; c < NK; ++c) {
                     mbar_expect_tx(full_w + c, WBYTES);
