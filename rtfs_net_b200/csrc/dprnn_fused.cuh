@@ -27,14 +27,13 @@
 namespace rtfs {
 
 constexpr int DF_NP = 256;                 // largest tile (positions); sequences longer than this take the unfused path
-constexpr int DF_NSTG = 4;                 // regular weight-ring slots (and units a producer may run ahead of a phase)
-constexpr int DF_SLAB = 16384;             // one weight slab of the image (weights.py: dprnn_fused_image)
+constexpr int DF_SLAB = 16384;             // one weight slab of the image (weights.py: dprnn_fused_image) = one bulk copy
 constexpr int DF_NSLAB = 32 + 3 * 4 + 8;   // layer 0 | layers 1-3 | transposed conv
+constexpr int DF_NPROD = 4;                // weight-producer warps
 
-// Tile configuration.  NP = 256: one CTA of 512 threads per SM, 16 KB ring units.  NP = 128 (sequences of up to 128 steps):
-// 256 threads and 110 KB of shared memory, so TWO tiles are resident per SM (2 x 256 TMEM columns) and one tile's serial
-// recurrence / load / store phases run under the other tile's UMMAs; the weight ring moves 8 KB half-slabs (accumulator 0's
-// and accumulator 1's K-channels of a slab, or K-pieces 0-7 / 8-15 of a transposed-conv tap).
+// Tile configuration.  NP = 256: one CTA of 512 threads per SM.  NP = 128 (sequences of up to 128 steps): 256 threads and 102 KB of
+// shared memory per pipeline, so two tiles are resident per SM (2 x 256 TMEM columns) and one tile's serial recurrence / load /
+// store phases run under the other tile's UMMAs.
 template <int NP>
 struct DfC {
     static constexpr int NT = 2 * NP;              // threads: 4 warps per 64 positions
@@ -43,36 +42,35 @@ struct DfC {
     static constexpr int LBO = ROWS * 16 + 16;     // bytes between 4-channel pieces (4336 / 2288: 112 mod 128)
     static constexpr int HBUF = 16 * LBO;
     static constexpr int CS = NP * 64 * 4;         // c_t of every (position, column)
-    static constexpr int UPS = NP == 256 ? 1 : 2;  // ring units per weight slab
-    static constexpr int WCH = DF_SLAB / UPS;      // ring unit bytes
-    static constexpr int NUNIT = DF_NSLAB * UPS;
-    static constexpr int SMEM = HBUF + CS + DF_NSTG * WCH + 2 * NP * 4 + 256 + 8 * 16 * 8;  // one pipeline
+    // Weight ring.  A bulk copy lands ~1000 cycles after it is issued and costs its issuing thread 300-500 cycles whatever its size, and
+    // a wait that has to suspend takes ~200 cycles to wake: the issuing thread must find its weights already landed.  So weights move
+    // as whole 16 KB slabs, dealt to four producer warps.  The ring proper holds NRING slabs; the c buffer directly below it is as
+    // large and idle until the first recurrence, so layer 0 -- 512 KB of weights per tile -- cycles through c buffer + ring
+    // (NSL = 2 NRING slab slots), the later layers through the ring.
+    static constexpr int NRING = CS / DF_SLAB;     // 2 (NP = 128) or 4
+    static constexpr int NSL = 2 * NRING;
+    static constexpr int SMEM = HBUF + CS + NRING * DF_SLAB + 2 * NP * 4 + 256 + 8 * 16 * 8;  // one pipeline
     static constexpr int MINB = NP == 256 ? 1 : 2;
-    // Weight ring.  A bulk copy lands ~1000 cycles after it is issued, so a 4-unit ring sustains ~30 B/clk -- half of what the
-    // layer-0 GEMM (512 KB of weights per tile) consumes at the tensor rate.  The c buffer (= 4 units, directly below the ring) is idle
-    // until the first recurrence, so layer 0 cycles through 8 slots (c buffer + ring), the later layers through the ring's 4.
-    static constexpr int NSLOT = 8;
-    static constexpr int L0U = 32 * UPS;  // layer-0 units per tile
-    static_assert(CS == 4 * WCH, "the c buffer holds exactly four ring units");
-    // every slot sees an even number of uses per tile (or the CTA runs one tile), so barrier parities do not depend on the tile
-    static_assert(NP == 256 || ((L0U / 8) % 2 == 0 && ((NUNIT - L0U) / 4) % 2 == 0), "ring parities must repeat per tile");
-    static_assert(L0U % 8 == 0 && (NUNIT - L0U) % 4 == 0 && NUNIT % 4 == 0, "units fill the slots evenly");
+    static_assert(CS == NRING * DF_SLAB && (NRING == 2 || NRING == 4), "the c buffer mirrors the ring");
+    // every slot sees an even number of uses per tile (or the CTA runs one tile), so wait parities do not depend on the tile
+    static_assert(NP == 256 || ((32 / NSL) % 2 == 0 && ((DF_NSLAB - 32) / NRING) % 2 == 0), "ring parities must repeat per tile");
 };
-constexpr int DF_NPROD = 4;
-// Slot (0-3: c buffer, 4-7: ring; also the index of its barriers) and wait parity of weight unit u of a tile.  Layer 0 starts on the
-// ring slots (its first units are fetched while the previous tile's epilogue still stages through the c buffer).  Producer p
-// (warp p + 1 of the pipeline) fetches the units u = p mod 4, which are exactly the uses of slots p and p + 4: every slot is
-// refilled by ONE thread, in order -- a parity wait is only sound while the waiter is at most one phase behind.
+// Slab slot ss (0 .. NRING-1: c buffer, NRING .. NSL-1: ring; also the index of its full_w / mma_done barriers), wait parity and owning
+// producer of weight slab i of a tile.  Layer 0 starts on the ring half (its first slabs are fetched while the previous tile's
+// epilogue still stages through the c buffer).  Every slot is refilled by ONE producer, in order: a parity wait is only sound while
+// the waiter is at most one phase behind, which a single in-order owner is by construction.
 template <int NP>
-DEVINL void df_unit_slot(int u, int& slot, uint32_t& par) {
+DEVINL void df_slab_slot(int i, int& ss, uint32_t& par, int& owner) {
     using C = DfC<NP>;
-    if (u < C::L0U) {
-        slot = (u + 4) & 7;
-        par = (uint32_t)(u >> 3) & 1u;
+    if (i < 32) {
+        ss = (i + C::NRING) & (C::NSL - 1);
+        par = (uint32_t)(i / C::NSL) & 1u;
+        owner = i & 3;  // = the owner of the later layers' slot when ss is a ring slot
     } else {
-        const int v = u - C::L0U;
-        slot = 4 + (v & 3);
-        par = (uint32_t)(v >> 2) & 1u;  // L0U / 8 earlier uses: an even number
+        const int v = i - 32;
+        ss = C::NRING + (v & (C::NRING - 1));
+        par = (uint32_t)(v / C::NRING) & 1u;  // an even number of layer-0 uses came before
+        owner = v & (C::NRING - 1);
     }
 }
 
@@ -210,7 +208,7 @@ template <int GATE, int NP, bool DUAL>
 __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::MINB) dprnn_fused_kernel(DfArgs a) {
     using C = DfC<NP>;
     static_assert(!DUAL || NP == 128, "the two-pipeline kernel runs 128-position tiles");
-    constexpr int DF_NT = C::NT, DF_LBO = C::LBO, DF_HBUF = C::HBUF, DF_CS = C::CS, DF_WCH = C::WCH, UPS = C::UPS;
+    constexpr int DF_NT = C::NT, DF_LBO = C::LBO, DF_HBUF = C::HBUF, DF_CS = C::CS;
     constexpr int NW = DF_NT / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int half = DUAL ? (int)(threadIdx.x >> 8) : 0;
@@ -219,14 +217,14 @@ __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::
     unsigned char* hbuf = sm;
     float* cs = reinterpret_cast<float*>(sm + DF_HBUF);
     unsigned char* wring = sm + DF_HBUF + DF_CS;
-    int* pos2off = reinterpret_cast<int*>(wring + DF_NSTG * DF_WCH);  // [2][NP]: double-buffered over tiles
+    int* pos2off = reinterpret_cast<int*>(wring + C::NRING * DF_SLAB);  // [2][NP]: double-buffered over tiles
     uint64_t* full_w = reinterpret_cast<uint64_t*>(pos2off + 2 * NP);
-    uint64_t* mma_done = full_w + C::NSLOT;
-    uint64_t* acc_ready = mma_done + C::NSLOT;
-    static_assert((2 * C::NSLOT + 1) * 8 + 32 <= 256, "barriers + seqstat fit their 256 bytes");
+    uint64_t* mma_done = full_w + 8;
+    uint64_t* acc_ready = mma_done + 8;
+    static_assert((2 * 8 + 1) * 8 + 32 <= 256, "barriers + seqstat fit their 256 bytes");
     float* seqstat = reinterpret_cast<float*>(acc_ready + 1);  // [4 sequences][mean, rstd] of the gLN applied when first
     // chunk_bar[(sequence, direction)][16-step block]: c-recurrence warp -> h warp hand-off, one completion per layer
-    uint64_t* chunk_bar = reinterpret_cast<uint64_t*>(sm + DF_HBUF + DF_CS + DF_NSTG * DF_WCH + 2 * NP * 4 + 256);
+    uint64_t* chunk_bar = reinterpret_cast<uint64_t*>(sm + DF_HBUF + DF_CS + C::NRING * DF_SLAB + 2 * NP * 4 + 256);
     // shared by both pipelines: the layer-0 hand-off barriers and the TMEM base
     uint64_t* l0_done = reinterpret_cast<uint64_t*>(smem_raw + (DUAL ? 2 : 1) * C::SMEM);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(l0_done + 2);
@@ -252,7 +250,7 @@ __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::
     // barrier initialisation before anything is in flight: its release fence would otherwise wait for the loads below
     if (tid == 32) {
 #pragma unroll
-        for (int s = 0; s < C::NSLOT; ++s) {
+        for (int s = 0; s < 8; ++s) {
             mbar_init(full_w + s, 1);
             mbar_init(mma_done + s, 1);
         }
@@ -273,35 +271,37 @@ __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::
     tc_fence_after();
     const uint32_t tmem = *tmem_slot + (uint32_t)(half * 2 * NP);
 
-    // ---- weight producers (warps 1..DF_NPROD of the pipeline): unit G (counted over all tiles) -> image unit G % NUNIT, slot and
-    //      parity from df_unit_slot.  Called by the whole warp, one lane issues.
-    const int wtotal = niter * C::NUNIT;
+    // ---- weight producers (warps 1..DF_NPROD of the pipeline): slab n (counted over all tiles) -> df_slab_slot(n % DF_NSLAB); every
+    //      producer scans the slabs in order and issues the ones it owns.  Called by the whole warp, one lane issues.
+    const int wtotal = niter * DF_NSLAB;
     const bool is_prod = warp >= 1 && warp <= DF_NPROD;
-    int wnext = warp - 1;  // next unit of this producer, counted over all tiles
+    int wnext = 0, wi = 0;  // next slab to look at: index over all tiles / inside the tile
     auto produce_until = [&](int limit) {
         if (limit > wtotal) limit = wtotal;
         const bool lead = elect_one();
-        for (; wnext < limit; wnext += DF_NPROD) {
+        for (; wnext < limit; ++wnext) {
             if (lead) {
-                const int u = wnext % C::NUNIT;
-                int slot;
+                int ss, owner;
                 uint32_t par;
-                df_unit_slot<NP>(u, slot, par);
-                if (wnext >= C::NSLOT) mbar_wait(mma_done + slot, par ^ 1u);  // the slot's previous use has been multiplied
-                mbar_expect_tx(full_w + slot, DF_WCH);
-                bulk_g2s(reinterpret_cast<unsigned char*>(cs) + slot * DF_WCH, a.wimg + (size_t)u * (DF_WCH / 4), DF_WCH, full_w + slot);
+                df_slab_slot<NP>(wi, ss, par, owner);
+                if (owner == warp - 1) {
+                    mbar_wait(mma_done + ss, par ^ 1u);  // the previous use has been multiplied (passes at once on a fresh barrier)
+                    mbar_expect_tx(full_w + ss, DF_SLAB);
+                    bulk_g2s(reinterpret_cast<unsigned char*>(cs) + ss * DF_SLAB, a.wimg + (size_t)wi * (DF_SLAB / 4), DF_SLAB, full_w + ss);
+                }
             }
+            if (++wi == DF_NSLAB) wi = 0;
         }
         __syncwarp();
     };
-    if (is_prod) produce_until(DF_NSTG);
+    if (is_prod) produce_until(C::NRING);
 
     const int l16 = tid & 15, c = l16 * 4;
     // descriptors are advanced by integer adds on the (address >> 4) field: one 16-byte slab row = 1, one 4-channel piece = LBO / 16
     const uint64_t d_slab = umma_desc(smem_u32(hbuf), DF_LBO, 128);       // slab rows as the positions operand
     const uint64_t d_wsru = umma_desc(smem_u32(cs), 2048, 128);          // SRU weights (slot 0): 128 features x 4-channel pieces
     const uint64_t d_wct = umma_desc(smem_u32(cs), 1024, 128);           // transposed-conv weights: 64 outputs x 4-channel pieces
-    constexpr uint32_t PIECE = DF_LBO / 16, UNIT16 = DF_WCH / 16;
+    constexpr uint32_t PIECE = DF_LBO / 16, SLAB16 = DF_SLAB / 16;
     constexpr uint32_t IDESC_SRU = umma_idesc_tf32(128, NP);
     constexpr uint32_t IDESC_CT = umma_idesc_tf32(128, 64);
     const int p_lo = sw * S, p_hi = p_lo + L;
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::
         const int tile = DUAL ? (it * (int)gridDim.x + (int)blockIdx.x) * 2 + half : (int)blockIdx.x;  // tiles past the end run empty
         const int seq0 = tile * a.nseq_tile;
         int* p2o = pos2off + (it & 1) * NP;
-        const int ubase = it * C::NUNIT;
+        const int ibase = it * DF_NSLAB;  // slabs before this tile
         if (DUAL) {
             dbg_on = a.dbg != nullptr && tid == 0 && it == (niter > 1 ? 1 : 0);
             dbg_i = 0;
@@ -438,33 +438,25 @@ __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::
                         const uint32_t tap = ly == 0 ? (uint32_t)(gl >> 2) : 0u;
                         const uint32_t cb = (uint32_t)(ly == 0 ? (gl & 3) : gl) * 4u;
                         const uint64_t db = d_slab + (uint64_t)(cb * PIECE + 7u + tap);
-#pragma unroll
-                        for (int hf = 0; hf < UPS; ++hf) {  // UPS = 2: accumulator 0's 16 K-channels, then accumulator 1's
-                            int slot;
-                            uint32_t par;
-                            df_unit_slot<NP>((cbeg + gl) * UPS + hf, slot, par);
-                            mbar_wait(full_w + slot, par);
-                            tc_fence_after();
-                            const uint64_t da = d_wsru + (uint64_t)((uint32_t)slot * UNIT16);
-                            const uint32_t acc_on = gl > 0 ? 1u : 0u;
-                            if (UPS == 1) {
-                                umma_tf32(tmem, da, db, IDESC_SRU, acc_on);
-                                umma_tf32(tmem + NP, da + 512u, db, IDESC_SRU, acc_on);
-                                umma_tf32(tmem, da + 256u, db + 2u * PIECE, IDESC_SRU, 1u);
-                                umma_tf32(tmem + NP, da + 768u, db + 2u * PIECE, IDESC_SRU, 1u);
-                            } else {
-                                umma_tf32(tmem + hf * NP, da, db, IDESC_SRU, acc_on);
-                                umma_tf32(tmem + hf * NP, da + 256u, db + 2u * PIECE, IDESC_SRU, 1u);
-                            }
-                            umma_commit(mma_done + slot);
-                        }
+                        const uint32_t acc_on = gl > 0 ? 1u : 0u;
+                        int ss, owner;
+                        uint32_t par;
+                        df_slab_slot<NP>(cbeg + gl, ss, par, owner);
+                        mbar_wait(full_w + ss, par);
+                        tc_fence_after();
+                        const uint64_t da = d_wsru + (uint64_t)((uint32_t)ss * SLAB16);  // [accumulator 0 | 1][16 K-channels][128 features]
+                        umma_tf32(tmem, da, db, IDESC_SRU, acc_on);
+                        umma_tf32(tmem + NP, da + 512u, db, IDESC_SRU, acc_on);
+                        umma_tf32(tmem, da + 256u, db + 2u * PIECE, IDESC_SRU, 1u);
+                        umma_tf32(tmem + NP, da + 768u, db + 2u * PIECE, IDESC_SRU, 1u);
+                        umma_commit(mma_done + ss);
                     }
                     if (DUAL && ly == 0) umma_commit(l0_done + half);
                     umma_commit(acc_ready);
                 }
                 __syncwarp();
             } else if (is_prod) {
-                produce_until(ubase + (cbeg + nch) * UPS + DF_NSTG);
+                produce_until(ibase + cbeg + nch + C::NRING);
             }
             cbeg += nch;
             mbar_wait(acc_ready, nacc & 1);
@@ -557,31 +549,27 @@ __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::
         // ---- ConvTranspose1d: out[positions][64] = sum_kk slab[p + kk] . Wct_kk   (positions on the lanes)
         if (warp == 0) {
             if (elect_one()) {
-                for (int gl = 0; gl < 8; ++gl) {
+                for (int gl = 0; gl < 8; ++gl) {  // one slab = the 16 K-pieces (4 channels each) of tap gl
+                    int ss, owner;
+                    uint32_t par;
+                    df_slab_slot<NP>(cbeg + gl, ss, par, owner);
+                    mbar_wait(full_w + ss, par);
+                    tc_fence_after();
+                    const uint64_t dw = d_wct + (uint64_t)((uint32_t)ss * SLAB16);
 #pragma unroll
-                    for (int hf = 0; hf < UPS; ++hf) {  // a unit holds 16 / UPS K-pieces (4 channels each) of tap gl
-                        int slot;
-                        uint32_t par;
-                        df_unit_slot<NP>((cbeg + gl) * UPS + hf, slot, par);
-                        mbar_wait(full_w + slot, par);
-                        tc_fence_after();
-                        const uint64_t dw = d_wct + (uint64_t)((uint32_t)slot * UNIT16);
-#pragma unroll
-                        for (int kk = 0; kk < 8 / UPS; ++kk) {
-                            const uint32_t k8 = (uint32_t)(hf * (8 / UPS) + kk);
-                            const uint64_t dh = d_slab + (uint64_t)(2u * k8 * PIECE + (uint32_t)gl);
-                            const uint32_t acc_on = (gl > 0 || k8 > 0) ? 1u : 0u;
-                            umma_tf32(tmem, dh, dw + (uint64_t)(kk * 128), IDESC_CT, acc_on);
-                            if (NP == 256) umma_tf32(tmem + 64, dh + 128u, dw + (uint64_t)(kk * 128), IDESC_CT, acc_on);
-                        }
-                        umma_commit(mma_done + slot);
+                    for (int k8 = 0; k8 < 8; ++k8) {
+                        const uint64_t dh = d_slab + (uint64_t)(2u * (uint32_t)k8 * PIECE + (uint32_t)gl);
+                        const uint32_t acc_on = (gl > 0 || k8 > 0) ? 1u : 0u;
+                        umma_tf32(tmem, dh, dw + (uint64_t)(k8 * 128), IDESC_CT, acc_on);
+                        if (NP == 256) umma_tf32(tmem + 64, dh + 128u, dw + (uint64_t)(k8 * 128), IDESC_CT, acc_on);
                     }
+                    umma_commit(mma_done + ss);
                 }
                 umma_commit(acc_ready);
             }
             __syncwarp();
         } else if (is_prod) {
-            produce_until(ubase + C::NUNIT + DF_NSTG);  // runs ahead into the next tile's layer-0 units
+            produce_until(ibase + DF_NSLAB + C::NRING);  // runs ahead into the next tile's first layer-0 slabs (ring half only)
         }
         mbar_wait(acc_ready, nacc & 1);
         ++nacc;
