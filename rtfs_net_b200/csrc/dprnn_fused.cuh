@@ -52,17 +52,24 @@ struct DfC {
     static constexpr int SMEM = HBUF + CS + NRING * DF_SLAB + 2 * NP * 4 + 256 + 8 * 16 * 8;  // one pipeline
     static constexpr int MINB = NP == 256 ? 1 : 2;
     static_assert(CS == NRING * DF_SLAB && (NRING == 2 || NRING == 4), "the c buffer mirrors the ring");
-    // every slot sees an even number of uses per tile (or the CTA runs one tile), so wait parities do not depend on the tile
-    static_assert(NP == 256 || ((32 / NSL) % 2 == 0 && ((DF_NSLAB - 32) / NRING) % 2 == 0), "ring parities must repeat per tile");
 };
 // Slab slot ss (0 .. NRING-1: c buffer, NRING .. NSL-1: ring; also the index of its full_w / mma_done barriers), wait parity and owning
-// producer of weight slab i of a tile.  Layer 0 starts on the ring half (its first slabs are fetched while the previous tile's
-// epilogue still stages through the c buffer).  Every slot is refilled by ONE producer, in order: a parity wait is only sound while
-// the waiter is at most one phase behind, which a single in-order owner is by construction.
+// producer of weight slab i of tile `it` of the pipeline.  Every slot is refilled by ONE producer, in order: a parity wait is only
+// sound while the waiter is at most one phase behind, which a single in-order owner is by construction.
+//   NP = 128: ONE 4-slot ring over the whole tile, ss = (i + 2) & 3 -- slabs 0, 1 of the tile, of every later layer and of the
+//     transposed conv fall on the ring half (fetched ahead, while the c buffer holds c values or stages the epilogue), slabs 2, 3 of a
+//     later layer on the c-buffer half (requested the moment that layer's GEMM phase begins: the h phase has just released the
+//     buffer; they used to wait for slabs 0, 1 to be multiplied first).  52 slabs = 13 uses per slot and tile: parities flip per tile.
+//   NP = 256 (one tile per CTA): layer 0 through all 8 slots, the later layers through the ring's 4 (a whole layer fits).
 template <int NP>
-DEVINL void df_slab_slot(int i, int& ss, uint32_t& par, int& owner) {
+DEVINL void df_slab_slot(int i, int it, int& ss, uint32_t& par, int& owner) {
     using C = DfC<NP>;
-    if (i < 32) {
+    if (NP == 128) {
+        static_assert(NP != 128 || (DF_NSLAB % 4 == 0 && (DF_NSLAB / 4) % 2 == 1), "13 uses per slot and tile");
+        ss = (i + 2) & 3;
+        par = (uint32_t)((i >> 2) + it) & 1u;
+        owner = ss;
+    } else if (i < 32) {
         ss = (i + C::NRING) & (C::NSL - 1);
         par = (uint32_t)(i / C::NSL) & 1u;
         owner = i & 3;  // = the owner of the later layers' slot when ss is a ring slot
@@ -275,7 +282,7 @@ __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::
     //      producer scans the slabs in order and issues the ones it owns.  Called by the whole warp, one lane issues.
     const int wtotal = niter * DF_NSLAB;
     const bool is_prod = warp >= 1 && warp <= DF_NPROD;
-    int wnext = 0, wi = 0;  // next slab to look at: index over all tiles / inside the tile
+    int wnext = 0, wi = 0, wt = 0;  // next slab to look at: index over all tiles / inside the tile, its tile
     auto produce_until = [&](int limit) {
         if (limit > wtotal) limit = wtotal;
         const bool lead = elect_one();
@@ -283,14 +290,17 @@ __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::
             if (lead) {
                 int ss, owner;
                 uint32_t par;
-                df_slab_slot<NP>(wi, ss, par, owner);
+                df_slab_slot<NP>(wi, wt, ss, par, owner);
                 if (owner == warp - 1) {
                     mbar_wait(mma_done + ss, par ^ 1u);  // the previous use has been multiplied (passes at once on a fresh barrier)
                     mbar_expect_tx(full_w + ss, DF_SLAB);
                     bulk_g2s(reinterpret_cast<unsigned char*>(cs) + ss * DF_SLAB, a.wimg + (size_t)wi * (DF_SLAB / 4), DF_SLAB, full_w + ss);
                 }
             }
-            if (++wi == DF_NSLAB) wi = 0;
+            if (++wi == DF_NSLAB) {
+                wi = 0;
+                ++wt;
+            }
         }
         __syncwarp();
     };
@@ -441,7 +451,7 @@ __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::
                         const uint32_t acc_on = gl > 0 ? 1u : 0u;
                         int ss, owner;
                         uint32_t par;
-                        df_slab_slot<NP>(cbeg + gl, ss, par, owner);
+                        df_slab_slot<NP>(cbeg + gl, it, ss, par, owner);
                         mbar_wait(full_w + ss, par);
                         tc_fence_after();
                         const uint64_t da = d_wsru + (uint64_t)((uint32_t)ss * SLAB16);  // [accumulator 0 | 1][16 K-channels][128 features]
@@ -552,7 +562,7 @@ __global__ void __launch_bounds__(DUAL ? 512 : DfC<NP>::NT, DUAL ? 1 : DfC<NP>::
                 for (int gl = 0; gl < 8; ++gl) {  // one slab = the 16 K-pieces (4 channels each) of tap gl
                     int ss, owner;
                     uint32_t par;
-                    df_slab_slot<NP>(cbeg + gl, ss, par, owner);
+                    df_slab_slot<NP>(cbeg + gl, it, ss, par, owner);
                     mbar_wait(full_w + ss, par);
                     tc_fence_after();
                     const uint64_t dw = d_wct + (uint64_t)((uint32_t)ss * SLAB16);
