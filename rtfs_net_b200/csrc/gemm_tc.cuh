@@ -28,8 +28,24 @@ DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
 DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Potentially blocking test of a phase.  The suspend-time hint (ns) lets the hardware park the thread until the phase completes
+// or the time is up; without it the test returns almost at once and every waiting warp spins hot -- ncu on the mask + decoder GEMM
+// counted 60 % of all executed warp instructions in such loops (16 producer warps polling next to the 8 epilogue warps that
+// bound the kernel).  RTFS_MBAR_HINT_NS=0 at compile time restores the plain form for A/B runs.
+#ifndef RTFS_MBAR_HINT_NS
+#define RTFS_MBAR_HINT_NS 1000000
+#endif
 DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+#if RTFS_MBAR_HINT_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)RTFS_MBAR_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -37,13 +53,14 @@ DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+#endif
     return ok != 0;
 }
-// Bounded spin: a protocol bug traps instead of hanging the device.
+// Bounded wait: a protocol bug traps instead of hanging the device (2^14 tests of up to 1 ms each, or 2^24 plain ones).
 DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) __trap();
+        if (++spins > (RTFS_MBAR_HINT_NS > 0 ? (1u << 14) : (1u << 24))) __trap();
     }
 }
 // TMA engine bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
@@ -453,20 +470,21 @@ struct MaskDecEpi4 {
     static constexpr int kTcpEpiRegs = 104;
     static constexpr bool kRollPre = false;
     static constexpr bool kFusedRows = true;
+    static constexpr bool kPrefetchTile = true;
     static constexpr int kSmemBytes = 256 * 20 * 4;
     struct Pre {
         float2 er, ei;
     };
     float4 bi_;
     const float* wtab_;
-    float2 q_[9];  // the 18 partial products of this thread's row, packed for f32x2 FMAs
+    float2 q_[2][9];  // the 18 partial products of this lane's two rows, packed for f32x2 FMAs
     DEVINL void bind_smem(float* tab, int tid, int nthr) {
         for (int i = tid; i < 256 * 5; i += nthr) reinterpret_cast<float4*>(tab)[i] = ldg4(wdec + 4 * i);
         wtab_ = tab;
     }
     DEVINL void init(int, int) {
 #pragma unroll
-        for (int r = 0; r < 9; ++r) q_[r] = make_float2(0.f, 0.f);
+        for (int r = 0; r < 9; ++r) q_[0][r] = q_[1][r] = make_float2(0.f, 0.f);
     }
     DEVINL void prep(int col) { bi_ = ldg4(bias + col); }
     DEVINL Pre load(int row, int col) const {
@@ -484,48 +502,79 @@ struct MaskDecEpi4 {
         const float2 er = p.er, ei = p.ei;
         *reinterpret_cast<float4*>(slot) = make_float4(er.x * mr0 - ei.x * mi0, er.x * mi0 + ei.x * mr0, er.y * mr1 - ei.y * mi1, er.y * mi1 + ei.y * mr1);
     }
-    // thread = row: 32 staged z values of this block against the filter rows col0 .. col0 + 31 (9 packed FMAs per value)
-    DEVINL void block_reduce(const float* zrow, int col0) {
-        const float4* w = reinterpret_cast<const float4*>(wtab_ + col0 * 20);
+    // L2 prefetch of the a0 rows of a tile (128 rows x 1 KB = 1024 lines), issued by the 256 epilogue threads one tile ahead: the
+    // epilogue's a0 loads are exposed once per 32-column block, and an L2 hit costs a third of a DRAM round trip under load
+    DEVINL void prefetch_tile(int row0, int M, int tid) const {
+        const char* base = reinterpret_cast<const char*>(a0 + (long long)row0 * 256);
+        const long long lim = ((long long)M - row0) * 1024;  // bytes of a0 from row0 to the end
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long off = (long long)(tid + 256 * i) * 128;
+            if (off < lim) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+        }
+    }
+    // The decoder taps of the 32 staged z columns of this block.  Lane = (row pair rp = lane & 15, column parity cp = lane >> 4):
+    // rows 2 rp, 2 rp + 1 of the warp's 32 against the filter rows of columns col0 + cp, col0 + 2 + cp, ...: every filter row read
+    // from shared memory feeds 18 packed FMAs instead of 9 (the kernel was bound by these loads: ncu `mio` stalls on LDS, 5 loads per
+    // 9 FMAs with one row per lane), and the two parities read rows 20 floats apart, i.e. disjoint banks.
+    DEVINL void block_reduce(const float* stg, int lane, int col0) {
+        const int rp = lane & 15, cp = lane >> 4;
+        const float* z0 = stg + (2 * rp) * TC_STG_LD;
+        const float4* w = reinterpret_cast<const float4*>(wtab_ + (col0 + cp) * 20);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 z4 = *reinterpret_cast<const float4*>(zrow + 4 * j4);
-            const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+            const float4 a = *reinterpret_cast<const float4*>(z0 + 4 * j4);
+            const float4 b = *reinterpret_cast<const float4*>(z0 + TC_STG_LD + 4 * j4);
+            const float za[2] = {cp ? a.y : a.x, cp ? a.w : a.z};
+            const float zb[2] = {cp ? b.y : b.x, cp ? b.w : b.z};
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const float4* wr = w + (4 * j4 + jj) * 5;
+            for (int jj = 0; jj < 2; ++jj) {
+                const float4* wr = w + (4 * j4 + 2 * jj) * 5;
                 const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
                 const float2 w4 = *reinterpret_cast<const float2*>(wr + 4);
-                const float2 z = make_float2(zz[jj], zz[jj]);
-                q_[0] = __ffma2_rn(z, make_float2(w0.x, w0.y), q_[0]);
-                q_[1] = __ffma2_rn(z, make_float2(w0.z, w0.w), q_[1]);
-                q_[2] = __ffma2_rn(z, make_float2(w1.x, w1.y), q_[2]);
-                q_[3] = __ffma2_rn(z, make_float2(w1.z, w1.w), q_[3]);
-                q_[4] = __ffma2_rn(z, make_float2(w2.x, w2.y), q_[4]);
-                q_[5] = __ffma2_rn(z, make_float2(w2.z, w2.w), q_[5]);
-                q_[6] = __ffma2_rn(z, make_float2(w3.x, w3.y), q_[6]);
-                q_[7] = __ffma2_rn(z, make_float2(w3.z, w3.w), q_[7]);
-                q_[8] = __ffma2_rn(z, w4, q_[8]);
+                const float2 wv[9] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w), make_float2(w2.x, w2.y),
+                                      make_float2(w2.z, w2.w), make_float2(w3.x, w3.y), make_float2(w3.z, w3.w), w4};
+                const float2 ya = make_float2(za[jj], za[jj]), yb = make_float2(zb[jj], zb[jj]);
+#pragma unroll
+                for (int r = 0; r < 9; ++r) {
+                    q_[0][r] = __ffma2_rn(ya, wv[r], q_[0][r]);
+                    q_[1][r] = __ffma2_rn(yb, wv[r], q_[1][r]);
+                }
             }
         }
     }
-    // combine the two column halves of a row (warps q and q + 4) through the upper half's staging tile and store Q18
-    DEVINL void tile_done(float* stg_all, int warp, int lane, int row, int M) {
+    // fold the two column parities of a row pair (lanes l, l ^ 16), then the two column halves of the tile (warps q and q + 4, through
+    // the upper half's staging tile) and store Q18; row0w = first row of the warp's 32
+    DEVINL void tile_done(float* stg_all, int warp, int lane, int row0w, int M) {
         const int q = warp & 3, hlf = warp >> 2;
-        float* mine = stg_all + warp * (32 * TC_STG_LD) + lane * TC_STG_LD;
-        if (hlf == 1) {
 #pragma unroll
-            for (int r = 0; r < 9; ++r) *reinterpret_cast<float2*>(mine + 2 * r) = q_[r];
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int r = 0; r < 9; ++r) {
+                q_[h][r].x += __shfl_xor_sync(0xffffffffu, q_[h][r].x, 16);
+                q_[h][r].y += __shfl_xor_sync(0xffffffffu, q_[h][r].y, 16);
+            }
+        if (hlf == 1 && lane < 16) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float* mine = stg_all + warp * (32 * TC_STG_LD) + (2 * lane + h) * TC_STG_LD;
+#pragma unroll
+                for (int r = 0; r < 9; ++r) *reinterpret_cast<float2*>(mine + 2 * r) = q_[h][r];
+            }
         }
         named_bar_sync(4 + q, 64);
-        if (hlf == 0) {
-            const float* other = stg_all + (warp + 4) * (32 * TC_STG_LD) + lane * TC_STG_LD;
-            if (row < M) {
-                float* dst = q18 + (long long)row * 18;
+        if (hlf == 0 && lane < 16) {
 #pragma unroll
-                for (int r = 0; r < 9; ++r) {
-                    const float2 o = *reinterpret_cast<const float2*>(other + 2 * r);
-                    *reinterpret_cast<float2*>(dst + 2 * r) = make_float2(q_[r].x + o.x, q_[r].y + o.y);
+            for (int h = 0; h < 2; ++h) {
+                const int row = row0w + 2 * lane + h;
+                const float* other = stg_all + (warp + 4) * (32 * TC_STG_LD) + (2 * lane + h) * TC_STG_LD;
+                if (row < M) {
+                    float* dst = q18 + (long long)row * 18;
+#pragma unroll
+                    for (int r = 0; r < 9; ++r) {
+                        const float2 o = *reinterpret_cast<const float2*>(other + 2 * r);
+                        *reinterpret_cast<float2*>(dst + 2 * r) = make_float2(q_[h][r].x + o.x, q_[h][r].y + o.y);
+                    }
                 }
             }
         }
@@ -627,6 +676,14 @@ struct ep_roll<EP, decltype((void)EP::kRollPre)> {
 };
 
 // epilogues that consume whole rows through the staging tile (fused S^3 mask + decoder) and own a shared-memory table
+template <class EP, class = void>
+struct ep_prefetch {
+    static constexpr bool value = false;
+};
+template <class EP>
+struct ep_prefetch<EP, decltype((void)EP::kPrefetchTile)> {
+    static constexpr bool value = EP::kPrefetchTile;
+};
 template <class EP, class = void>
 struct ep_fused_rows {
     static constexpr bool value = false;

@@ -144,9 +144,15 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
                 }
             }
         }
+        if constexpr (ep_prefetch<EP>::value) {
+            if ((int)blockIdx.x < ntiles) ep.prefetch_tile(blockIdx.x * TC_BM, M, tid);
+        }
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int acc = it & 1, row0 = tile * TC_BM;
             ep.init(row0, M);
+            if constexpr (ep_prefetch<EP>::value) {  // the next tile's epilogue inputs on their way to L2 while this one is processed
+                if (tile + (int)gridDim.x < ntiles) ep.prefetch_tile((tile + (int)gridDim.x) * TC_BM, M, tid);
+            }
             mbar_wait(tmem_full + acc, (it >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -211,14 +217,14 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
                 }
                 __syncwarp();
                 if constexpr (FUSED) {
-                    ep.block_reduce(stg + lane * TC_STG_LD, col0);
+                    ep.block_reduce(stg, lane, col0);
                     __syncwarp();
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cta(tmem_empty + acc);  // this warp's TMEM reads of the accumulator are complete
-            if constexpr (FUSED) ep.tile_done(stg_all, warp, lane, row0 + q * 32 + lane, M);
+            if constexpr (FUSED) ep.tile_done(stg_all, warp, lane, row0 + q * 32, M);
             ep.finish_group(scratch, tid, TCP_EPI, 1);
         }
     } else if (warp < MMA_WARP) {

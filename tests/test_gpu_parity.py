@@ -371,13 +371,17 @@ def test_kernel_generations_agree(golden_sd):
         ("old", {"RTFS_LEGACY_GEMM": "1", "RTFS_LEGACY_DW": "1", "RTFS_UNFUSED_CAF": "1", "RTFS_NO_VIDEO_GRAPH": "1", "RTFS_LEGACY_FRONTEND": "1"}),
         # second generation: tcgen05 GEMMs one tile per CTA, unfused RNN around them, scalar TF-AR conv, mma.sync attention convs
         ("mid", {"RTFS_PERSIST_MASK": "0", "RTFS_UNFUSED_DPRNN": "1", "RTFS_SCALAR_TFAR": "1", "RTFS_LEGACY_ATT": "1", "RTFS_LEGACY_FRONTEND": "1"}),
+        # fused RNN tilings: one 256-position tile per CTA everywhere (round-1 shape) / 128-position tiles as independent CTAs;
+        # the default runs two 128-position pipelines per persistent CTA (dprnn_fused.cuh)
+        ("df256", {"RTFS_DF_TILE": "256"}),
+        ("df128", {"RTFS_DF_TILE": "128"}),
     )
     for tag, env in variants:
         path = os.path.join(ROOT, "gpurun_out", f"gen_{tag}.pt")
         os.makedirs(os.path.dirname(path), exist_ok=True)
         subprocess.run([sys.executable, "-c", code, path], check=True, env={**os.environ, **env}, timeout=600)
         outs[tag] = torch.load(path)
-    for tag in ("old", "mid"):
+    for tag in ("old", "mid", "df256", "df128"):
         e = rel_l2(outs["new"], outs[tag])
         report(f"kernel generations new vs {tag} rel_l2={e:.3e}")
         assert e <= 1e-3
