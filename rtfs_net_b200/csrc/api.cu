@@ -744,7 +744,7 @@ int run_block(const Ctx& c, const float* x, const float* addend, float* out, boo
             ResidOutCafEpi4 ep{out, P[RTFS_P_RC_B], x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], addend,
                                c.buf(RTFS_WS_VK), c.buf(RTFS_WS_ATT), P[RTFS_P_CAF_SK], P[RTFS_P_CAF_TK], P[RTFS_P_CAF_SV], P[RTFS_P_CAF_TV],
                                d.T, d.F, d.Tv, 0.f};
-            CK((launch_gemm_tc<256, 64, 2, 2, 2, 256>(al, P[RTFS_P_RC_WI], ep, M, c.st)));  // (the persistent kernel's 96-register cap spills this epilogue)
+            CK((launch_gemm_tc<256, 64, 2, 2, 2, 256>(al, P[RTFS_P_RC_WI], ep, M, c.st)));  // (the persistent kernel's 96-register cap spills this epilogue: measured 1.18 vs 0.76 ms)
         } else if (use_tc()) {
             ResidOutEpi4 ep{out, P[RTFS_P_RC_B], x, P[RTFS_P_GW_W], P[RTFS_P_GW_B], P[RTFS_P_GW_A], addend, 0.f};
             if (use_persistent(2)) CK((launch_gemm_tcp<256, 64, 4, 1, true, 2, 0, 256>(al, P[RTFS_P_RC_WI], ep, M, c.st)));
