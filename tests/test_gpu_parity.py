@@ -515,3 +515,25 @@ def test_video_block_kernel(model, golden_sd, O, Tv):
     report(f"video block kernel Tv={Tv} rel_l2={e:.3e} (torch modules on the GPU: {rel_l2(torch_path, ref):.3e})")
     assert out.shape == ref.shape
     assert e < TOL_FP32
+
+
+def test_streaming_separator_matches_direct_calls(golden_sd):
+    """shard.StreamingSeparator (double-buffered host -> device -> host loop, the bench's end-to-end leg): five different host
+    batches come back equal to the direct model calls, whatever the slot reuse."""
+    from rtfs_net_b200 import shard
+
+    m = build_model(golden_sd, 4)
+    g = torch.Generator().manual_seed(77)
+    B, L, Tv = 3, 16000, 25
+    batches = [((0.1 * torch.randn(B, L, generator=g)).pin_memory(), torch.rand(B, 512, Tv, generator=g).pin_memory(), torch.empty(B, 1, L).pin_memory())
+               for _ in range(5)]
+    sep = shard.StreamingSeparator(m, B, L, Tv)
+    for w, l, o in batches:
+        sep.submit(w, l, o)
+    sep.drain()
+    with torch.no_grad():
+        for i, (w, l, o) in enumerate(batches):
+            ref = m(w.cuda(), l.cuda()).cpu()
+            e = rel_l2(o, ref)
+            report(f"streaming separator batch {i} vs direct call rel_l2={e:.3e}")
+            assert e <= 1e-5  # same kernels, same batch position: differences only from the order of the fp64 statistics atomics
