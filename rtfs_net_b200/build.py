@@ -73,7 +73,8 @@ def build(force=False, verbose=False):
     os.makedirs(LIB_DIR, exist_ok=True)
     units = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
     tmp = LIB_PATH + ".tmp"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + units
+    extra = os.environ.get("RTFS_NVCC_EXTRA", "").split()  # e.g. -DRTFS_TCP_TRACE (epilogue phase stamps), -DRTFS_MBAR_HINT_NS=0
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + units
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

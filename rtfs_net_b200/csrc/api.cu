@@ -866,6 +866,18 @@ int run_mask_dec(const Ctx& c, const float* refined, const float* a0) {
     MaskDecEpi4 ep{c.buf(RTFS_WS_Q18), c.P[RTFS_P_MK_B], a0, c.P[RTFS_P_DEC_WT]};
     STAGE(RTFS_SG_MASK_DEC);
     CK((launch_gemm_tcp<256, 256, 3, 3, false, 4, 2, 512>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
+#ifdef RTFS_TCP_TRACE
+    {
+        long long h[64];
+        CKN(cudaStreamSynchronize(c.st));
+        CKN(cudaMemcpyFromSymbol(h, g_tcp_trace, sizeof(h)));
+        fprintf(stderr, "mask_dec epilogue warp 0, third tile: wait tmem_full %lld |", h[1] - h[0]);
+        for (int cb = 0; cb < 4; ++cb)
+            fprintf(stderr, " block %d: issue loads %lld, tmem + stage %lld, inputs + transform %lld, reduce %lld |", cb, h[2 + 5 * cb] - (cb ? h[5 * cb] : h[1]),
+                    h[3 + 5 * cb] - h[2 + 5 * cb], h[4 + 5 * cb] - h[3 + 5 * cb], h[5 + 5 * cb] - h[4 + 5 * cb]);
+        fprintf(stderr, " tile_done %lld, tile total %lld\n", h[30] - h[20], h[30] - h[0]);
+    }
+#endif
     return 0;
 }
 

@@ -56,6 +56,15 @@ __host__ __device__ constexpr int tcp_smem_bytes(int extra_floats) {
 //      ~3.4 TB/s on this part whatever the depth (tools/probe/cpasync_probe.cu), plain loads at 5.7-5.9 TB/s
 //   2  flat raw register stream: PF chunks of RAW values in flight per thread, running ahead across tile boundaries;
 //      the loader's xform() is applied when a chunk is stored (loaders with raw()/xform(): gLN-act, gateway, PReLU)
+#ifdef RTFS_TCP_TRACE  // build with RTFS_NVCC_EXTRA=-DRTFS_TCP_TRACE: clock64 stamps of epilogue warp 0 of CTA 0 in its third tile
+__device__ long long g_tcp_trace[64];
+#define TCP_STAMP(i)                                                                            \
+    do {                                                                                        \
+        if (blockIdx.x == 0 && tid == 0 && it == 2) g_tcp_trace[i] = clock64();                 \
+    } while (0)
+#else
+#define TCP_STAMP(i)
+#endif
 template <int BN, int KTOT, int NSA, int NSW, bool WRES, int PF, int ASYNC, int NPROD, class AL, class EP>
 __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al, const float* __restrict__ Wimg, EP ep, int M, int ntiles) {
     constexpr int TCP_PROD = NPROD;             // 256 or 512 producer threads
@@ -153,8 +162,10 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
             if constexpr (ep_prefetch<EP>::value) {  // the next tile's epilogue inputs on their way to L2 while this one is processed
                 if (tile + (int)gridDim.x < ntiles) ep.prefetch_tile((tile + (int)gridDim.x) * TC_BM, M, tid);
             }
+            TCP_STAMP(0);
             mbar_wait(tmem_full + acc, (it >> 1) & 1);
             tc_fence_after();
+            TCP_STAMP(1);
 #pragma unroll 1
             for (int cb = 0; cb < BN / 64; ++cb) {
                 const int col0 = hlf * (BN / 2) + cb * 32;
@@ -177,6 +188,7 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
                         }
                     }
                 }
+                TCP_STAMP(2 + 5 * cb);  // loads issued
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     uint32_t v[16];
@@ -192,6 +204,7 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
 #endif
                 }
                 __syncwarp();
+                TCP_STAMP(3 + 5 * cb);  // accumulator block staged
 #pragma unroll
                 for (int p = 0; p < 8; ++p) {
                     const int r = p * 4 + rsub;
@@ -216,16 +229,19 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
                     }
                 }
                 __syncwarp();
+                TCP_STAMP(4 + 5 * cb);  // epilogue inputs arrived, block transformed
                 if constexpr (FUSED) {
                     ep.block_reduce(stg, lane, col0);
                     __syncwarp();
                 }
+                TCP_STAMP(5 + 5 * cb);  // fused row reduction done
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cta(tmem_empty + acc);  // this warp's TMEM reads of the accumulator are complete
             if constexpr (FUSED) ep.tile_done(stg_all, warp, lane, row0 + q * 32, M);
             ep.finish_group(scratch, tid, TCP_EPI, 1);
+            TCP_STAMP(30);
         }
     } else if (warp < MMA_WARP) {
         if constexpr (REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
