@@ -230,7 +230,8 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
                 }
                 __syncwarp();
                 TCP_STAMP(4 + 5 * cb);  // epilogue inputs arrived, block transformed
-                if constexpr (FUSED) {
+                if constexpr (FUSED) {  // (running the previous block's reduction under this block's loads was measured: the 8 Pre
+                                        // registers sets live across it spill, 1.24 vs 0.78 ms)
                     ep.block_reduce(stg, lane, col0);
                     __syncwarp();
                 }
@@ -245,6 +246,9 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
         }
     } else if (warp < MMA_WARP) {
         if constexpr (REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        // 56 is forced: setmaxnreg moves registers inside the CTA's own launch allocation (26 warps x 72), so 8 x 104 + 16 x p + 2 x 72 <= 26 x 72
+        // gives p <= 56 (p = 64 deadlocks the epilogue's TRY_ALLOC).  At 56 the producers spill ~10 prefetch registers (SASS: STL / LDL only
+        // behind USETMAXREG.DEALLOC).
         if constexpr (REGSPLIT16) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         // ================================================================= A producers
         const int ptid = tid - TCP_EPI;
