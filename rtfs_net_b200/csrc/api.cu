@@ -850,7 +850,7 @@ int run_mask(const Ctx& c, const float* refined, const float* a0, float* z, floa
         CK((launch_gemm_tc<256, 256, 3, 1, 4, 256>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
     } else if (use_tc()) {
         MaskEpi4 ep{z, c.P[RTFS_P_MK_B], a0, nullptr};
-        if (use_persistent(3)) CK((launch_gemm_tcp<256, 256, 3, 4, false, 4, 2, 512>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
+        if (use_persistent(3)) CK((launch_gemm_tcp<256, 256, 3, 4, false, 2, 2, 512>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));  // prefetch depth 2: see run_mask_dec
         else CK((launch_gemm_tc<256, 256, 3, 1, 4, 256>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
     } else {
         MaskEpi ep{z, c.P[RTFS_P_MK_B], a0};
@@ -865,7 +865,7 @@ int run_mask_dec(const Ctx& c, const float* refined, const float* a0) {
     PreluLoader al{refined, c.P[RTFS_P_MK_A], 256};
     MaskDecEpi4 ep{c.buf(RTFS_WS_Q18), c.P[RTFS_P_MK_B], a0, c.P[RTFS_P_DEC_WT]};
     STAGE(RTFS_SG_MASK_DEC);
-    CK((launch_gemm_tcp<256, 256, 3, 3, false, 4, 2, 512>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));
+    CK((launch_gemm_tcp<256, 256, 3, 3, false, 2, 2, 512>(al, c.P[RTFS_P_MK_WI], ep, (int)(d.B * d.P), c.st)));  // prefetch depth 2: at 4 the 56-register producers spill
 #ifdef RTFS_TCP_TRACE
     {
         long long h[64];

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
     constexpr bool REGSPLIT16 = NPROD == 512 && ep_epi_regs<EP>::value > 0;
     if (warp < 8) {
         if constexpr (REGSPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
-        if constexpr (REGSPLIT16) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        if constexpr (REGSPLIT16) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ep_epi_regs<EP>::value));
         // ================================================================= epilogue
         const int q = warp & 3, hlf = warp >> 2;
         float* stg = stg_all + warp * (32 * TC_STG_LD);
@@ -230,8 +230,8 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
                 }
                 __syncwarp();
                 TCP_STAMP(4 + 5 * cb);  // epilogue inputs arrived, block transformed
-                if constexpr (FUSED) {  // (running the previous block's reduction under this block's loads was measured: the 8 Pre
-                                        // registers sets live across it spill, 1.24 vs 0.78 ms)
+                if constexpr (FUSED) {  // (running the previous block's reduction under this block's loads was measured twice: the 8 Pre
+                                        // register sets live across it spill at 104 and at 120 epilogue registers, 1.24 / 1.09 vs 0.74 ms)
                     ep.block_reduce(stg, lane, col0);
                     __syncwarp();
                 }
@@ -246,10 +246,11 @@ __global__ void __launch_bounds__(TCP_EPI + NPROD + 64, 1) gemm_tcp_kernel(AL al
         }
     } else if (warp < MMA_WARP) {
         if constexpr (REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-        // 56 is forced: setmaxnreg moves registers inside the CTA's own launch allocation (26 warps x 72), so 8 x 104 + 16 x p + 2 x 72 <= 26 x 72
-        // gives p <= 56 (p = 64 deadlocks the epilogue's TRY_ALLOC).  At 56 the producers spill ~10 prefetch registers (SASS: STL / LDL only
-        // behind USETMAXREG.DEALLOC).
-        if constexpr (REGSPLIT16) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        // setmaxnreg moves registers inside the CTA's own launch allocation (26 warps x 72): 8 E + 16 p + 2 x 72 <= 26 x 72, i.e. the
+        // producers get p = 108 - E / 2 (E = 104 -> 56, E = 120 -> 48; more deadlocks the epilogue's TRY_ALLOC).  At a register
+        // prefetch depth of 4 chunks the 56-register producers spilled (SASS: STL / LDL only behind USETMAXREG.DEALLOC): such kernels
+        // are launched with PF = 2.
+        if constexpr (REGSPLIT16) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(108 - ep_epi_regs<EP>::value / 2));
         // ================================================================= A producers
         const int ptid = tid - TCP_EPI;
         const int kq = ptid & 7;
