@@ -85,10 +85,10 @@ def test_bottleneck(model, golden_sd, O):
 
 
 @pytest.mark.parametrize("which,dim", [(0, 4), (1, 3)])
-@pytest.mark.parametrize("Tc", [125, 63])
-def test_dprnn(model, golden_sd, O, which, dim, Tc):
+@pytest.mark.parametrize("Tc,B", [(125, 2), (63, 2), (50, 3), (126, 1)])  # odd tile counts, half-empty last tiles, one utterance
+def test_dprnn(model, golden_sd, O, which, dim, Tc, B):
     g = torch.Generator().manual_seed(3 + which)
-    x = torch.randn(2, 64, Tc, 64, generator=g)
+    x = torch.randn(B, 64, Tc, 64, generator=g)
     with torch.no_grad():
         ref = O.dual_path_rnn(golden_sd, BLK + f"globalatt.{which}.", x, dim)
         out = model.refinement_module.audio_net.blocks.globalatt[which](x.cuda())
