@@ -317,3 +317,46 @@ def test_trainer_step_decreases_loss(golden_sd):
     report("trainer losses: " + " ".join(f"{v:.4f}" for v in losses))
     assert all(torch.isfinite(torch.tensor(losses)))
     assert losses[-1] < losses[0]
+
+
+def test_fast_sync_batchnorm_native_path_matches_batchnorm():
+    """train.FastSyncBatchNorm on CUDA (torch's fused batch-norm kernels around one collective, no host round trip) in a one-rank
+    NCCL group against BatchNorm1d: output, input / parameter gradients, running statistics."""
+    import torch.distributed as dist
+
+    from rtfs_net_b200.train import FastSyncBatchNorm, use_fast_sync_batchnorm
+
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29577")
+        dist.init_process_group("nccl", rank=0, world_size=1)
+        created = True
+    try:
+        g = torch.Generator().manual_seed(5)
+        x0 = (torch.randn(4, 512, 50, generator=g) * 1.5 + 0.3).cuda()
+        dy = torch.randn(4, 512, 50, generator=g).cuda()
+        net = torch.nn.Sequential(torch.nn.SyncBatchNorm(512)).cuda()
+        assert use_fast_sync_batchnorm(net) == 1
+        bn = net[0]
+        bn.force_sync = True
+        ref = torch.nn.BatchNorm1d(512).cuda()
+        with torch.no_grad():
+            bn.weight.normal_(1.0, 0.2)
+            bn.bias.normal_(0.0, 0.2)
+            ref.weight.copy_(bn.weight)
+            ref.bias.copy_(bn.bias)
+        bn.train()
+        ref.train()
+        x = x0.clone().requires_grad_(True)
+        xr = x0.clone().requires_grad_(True)
+        y, yr = bn(x), ref(xr)
+        y.backward(dy)
+        yr.backward(dy)
+        errs = dict(y=rel_l2(y, yr), dx=rel_l2(x.grad, xr.grad), dw=rel_l2(bn.weight.grad, ref.weight.grad), db=rel_l2(bn.bias.grad, ref.bias.grad),
+                    rm=rel_l2(bn.running_mean, ref.running_mean), rv=rel_l2(bn.running_var, ref.running_var))
+        report("fast SyncBatchNorm (native CUDA path) vs BatchNorm1d: " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+        assert max(errs.values()) < 1e-5 and int(bn.num_batches_tracked) == int(ref.num_batches_tracked)
+    finally:
+        if created:
+            dist.destroy_process_group()

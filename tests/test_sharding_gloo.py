@@ -111,3 +111,56 @@ def test_two_rank_gloo_training_exchange():
     mp.spawn(_train_worker, args=(world, port, ret), nprocs=world, join=True)
     assert ret["grad_ok"] and ret["pad_zero"]
     assert ret["pack"] == [0.0, 3.0, 6.0, 9.0, 12.0, 15.0, 30.0]
+
+
+def _syncbn_worker(rank, world, port, ret):
+    """train.FastSyncBatchNorm on two gloo ranks against one BatchNorm1d over the concatenated batch."""
+    import sys
+
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    from rtfs_net_b200 import shard
+    from rtfs_net_b200.train import FastSyncBatchNorm, use_fast_sync_batchnorm
+
+    shard.init("gloo")
+    g = torch.Generator().manual_seed(11)
+    x_all = torch.randn(5, 6, 7, generator=g) * 2.0 + 0.5  # uneven shards: 3 + 2 utterances
+    dy_all = torch.randn(5, 6, 7, generator=g)
+    w0, b0 = torch.randn(6, generator=g), torch.randn(6, generator=g)
+    lo, hi = shard.shard_bounds(5, rank, world)
+    net = torch.nn.Sequential(torch.nn.SyncBatchNorm(6))
+    assert use_fast_sync_batchnorm(net) == 1 and type(net[0]) is FastSyncBatchNorm
+    bn = net[0]
+    with torch.no_grad():
+        bn.weight.copy_(w0)
+        bn.bias.copy_(b0)
+    bn.train()
+    x = x_all[lo:hi].clone().requires_grad_(True)
+    y = bn(x)
+    y.backward(dy_all[lo:hi])
+    gw, gb = bn.weight.grad.clone(), bn.bias.grad.clone()
+    dist.all_reduce(gw)
+    dist.all_reduce(gb)
+    ref = torch.nn.BatchNorm1d(6)
+    with torch.no_grad():
+        ref.weight.copy_(w0)
+        ref.bias.copy_(b0)
+    ref.train()
+    xr = x_all.clone().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(dy_all)
+    errs = [float((y - yr[lo:hi]).abs().max()), float((x.grad - xr.grad[lo:hi]).abs().max()), float((gw - ref.weight.grad).abs().max()),
+            float((gb - ref.bias.grad).abs().max()), float((bn.running_mean - ref.running_mean).abs().max()),
+            float((bn.running_var - ref.running_var).abs().max()), float(abs(int(bn.num_batches_tracked) - int(ref.num_batches_tracked)))]
+    ret[rank] = max(errs)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_fast_sync_batchnorm():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_syncbn_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert max(ret.values()) < 2e-5, dict(ret)
