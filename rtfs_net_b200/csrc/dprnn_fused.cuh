@@ -4,9 +4,9 @@
 //   g (B,Tc,Fc,64) --LN over C--> n --unfold(8) . W0--> U0 --scan--> h0 --W1--> U1 --scan--> ... h3
 //     --ConvTranspose1d(64,64,8) + bias + residual--> g'
 //
-// A CTA owns a tile of up to 256 positions = NSEQ whole sequences packed back to back (frequency path:
-// 4 x 64 bins of one frame each; time path: 2 x 125 frames of one bin each).  Everything between the
-// load of g and the store of g' stays on chip:
+// A tile = whole sequences packed back to back: 128 positions (2 x 64 frequency bins of one frame each / 1 x 125 frames of one
+// bin) for sequences of up to 128 steps, two such tiles in flight per persistent CTA (template DUAL, see the kernel's comment);
+// 256 positions, one tile per CTA, for longer sequences.  Everything between the load of g and the store of g' stays on chip:
 //   * the activation slab (n, then h0..h3 in place) lives in shared memory in the UMMA K-major no-swizzle
 //     layout with 7 guard rows either side; nn.Unfold(8) and the k=8 transposed conv are the SAME slab read
 //     through descriptors whose start address is advanced by `tap` rows (16 bytes each) -- no im2col;
@@ -15,10 +15,13 @@
 //         64-127 = highway projection (layer 0)
 //     so the serial recurrence reads its own TMEM lane, 16 time steps per tcgen05.ld: warps (4s+0, 4s+1) run
 //     the c-recurrence of sequence s (forward / backward halves), warps (4s+2, 4s+3) then form h in parallel;
-//   * weights stream through a 5-stage ring of 16 KB slabs (one cp.async.bulk each, 52 slabs per tile,
-//     prefetched across phase boundaries by a dedicated producer thread);
+//   * weights stream as 52 whole 16 KB slabs per tile (one cp.async.bulk, one wait, one commit each) through a ring that layer 0
+//     extends into the idle c buffer, dealt to four producer warps of which each slot has exactly one (DfC, df_slab_slot);
+//   * tcgen05.mma / commit are issued by the elect.sync lane of warp 0 with descriptors advanced by integer adds (gemm_tc.cuh:
+//     elect_one), and every waiting warp parks on its mbarrier (suspend-time hint);
 //   * the transposed conv runs with positions on the lanes, so its epilogue (bias + residual + store) is the
 //     coalesced transposed-through-shared-memory store of gemm_tc.cuh.
+// Measurements behind these choices: profiles/r02_df_probes.txt (tools/probe/dfgemm_probe.cu, dfissue_probe.cu); DESIGN.md 4.2.
 #pragma once
 #include <cstdlib>
 #include "common.cuh"
