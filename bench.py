@@ -54,8 +54,10 @@ def make_inputs(batch, seed):
 
 def measured_traffic(stage):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage's kernel at B=32 from the committed
-    ncu --set full capture (profiles/r01_traffic.json), or None."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    ncu --set full capture (profiles/r02_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")  # ncu capture of this round's kernels (tools/make_traffic.py)
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if not os.path.exists(p):
         return None
     with open(p) as f:
