@@ -255,7 +255,9 @@ long long rtfs_train_pass_plan(int B, int L, long long* offsets /* RTFS_WS_COUNT
  *   -- the host forms the batch-statistics scale/shift of key_embed / value_embed (all-reducing the sums under SyncBatchNorm)
  *      and stores them in the RTFS_P_CAF_SK/TK/SV/TV parameter slots --
  *   phase 1: CAF, remaining passes, S^3 mask, decoder -> out (B,L).
- * video = output of the video block (B,512,Tv). */
+ * video = output of the video block (B,512,Tv).  Phase 0 may be called with video = NULL: it then runs the audio-only part, and
+ * the CAF video vectors are submitted later as phase 2 (before phase 1) -- the host can enqueue the audio kernels first and
+ * prepare the video block's output while they run. */
 int rtfs_avnet_train_forward(const float* const* params, const float* wav, const float* video, float* out, void* tape,
                              int B, int L, int Tv, int repeats, int phase, void* stream);
 

@@ -583,11 +583,16 @@ int rtfs_avnet_train_forward(const float* const* params, const float* wav, const
         RUN(run_bottleneck(c0, a0, a1, false));
         c0.train = true;
         RUN(run_block(c0, a1, nullptr, blk0));
-        RUN(run_caf_video(c0, video));
+        if (video != nullptr) RUN(run_caf_video(c0, video));  // (NULL: the caller submits the video-dependent part as phase 2)
         double* cs = reinterpret_cast<double*>(t.tape + t.tp.off[RTFS_TP_CAFSUM]);
         CKN(cudaMemsetAsync(cs, 0, 256 * 2 * 8, t.st));
         chan_stats_kernel<<<grid_for(rows * 64, 4), 256, 0, t.st>>>(blk0, rows, cs);
         CK(cudaGetLastError());
+        return 0;
+    }
+    if (phase == 2) {
+        if (video == nullptr) return fail_msg("rtfs_avnet_train_forward(2): video missing");
+        RUN(run_caf_video(c0, video));
         return 0;
     }
     // phase 1: CAF with the batch-statistics scale / shift the host stored in the SK / TK / SV / TV slots

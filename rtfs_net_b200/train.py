@@ -130,8 +130,15 @@ class _AVNetFn(torch.autograd.Function):
         lib = _lib.lib()
         video = video.contiguous()
         with torch.cuda.device(dev):
-            _lib.check(lib.rtfs_avnet_train_forward(table, wav.data_ptr(), video.data_ptr(), out.data_ptr(), bufs.tape.data_ptr(),
-                                                    B, L, Tv, R, 0, _stream()), "rtfs_avnet_train_forward(0)")
+            early = getattr(rt, "_audio_phase0", None)
+            rt._audio_phase0 = None
+            if early is not None and early[0] == (B, L, Tv, R, wav.data_ptr(), bufs.tape.data_ptr()):
+                # forward_train enqueued the audio-only part before the video block ran (and keeps its slot tensors alive in `early`)
+                _lib.check(lib.rtfs_avnet_train_forward(table, wav.data_ptr(), video.data_ptr(), out.data_ptr(), bufs.tape.data_ptr(),
+                                                        B, L, Tv, R, 2, _stream()), "rtfs_avnet_train_forward(2)")
+            else:
+                _lib.check(lib.rtfs_avnet_train_forward(table, wav.data_ptr(), video.data_ptr(), out.data_ptr(), bufs.tape.data_ptr(),
+                                                        B, L, Tv, R, 0, _stream()), "rtfs_avnet_train_forward(0)")
             # ---- CAF BatchNorm statistics (layers/fusion.py:210-228): y = w*a per channel => mean_y = w*mean_a, var_y = w^2*var_a
             T = L // 128 + 1
             sums_l = bufs.tape_view("RTFS_TP_CAFSUM", 256 * 2 * 8, torch.float64).view(256, 2).clone()
@@ -243,13 +250,23 @@ def forward_train(rt, wav, mouth):
         wav = wav[:, 0]
     wav = wav.contiguous()
     rm = model.refinement_module
-    video = rm.video_net.get_block(0)(model.video_bottleneck(mouth.contiguous()))  # eager torch ops + autograd
     live = live_tensors(model)
     slots = prepare(live, wav.device, train=True)
+    # The audio-only part of the forward (encoder, bottleneck, first block pass) is enqueued BEFORE the video block: that block is
+    # ~150 eager library launches (more under SyncBatchNorm) and bound by the host, which now works while the GPU is busy.
+    B, L, Tv = wav.shape[0], wav.shape[1], mouth.shape[-1]
+    R = rm.audio_params["repeats"]
+    bufs = rt.train_buffers(B, L, Tv, R, wav.device)
+    slot_list = [slots[n] for n in _lib.PARAM_NAMES]
+    with torch.cuda.device(wav.device):
+        _lib.check(_lib.lib().rtfs_avnet_train_forward(_table(slot_list), wav.data_ptr(), None, None, bufs.tape.data_ptr(), B, L, Tv, R, 0, _stream()),
+                   "rtfs_avnet_train_forward(0, audio)")
+    rt._audio_phase0 = ((B, L, Tv, R, wav.data_ptr(), bufs.tape.data_ptr()), slot_list)
+    video = rm.video_net.get_block(0)(model.video_bottleneck(mouth.contiguous()))  # eager torch ops + autograd
     q = CAF
     bnp = [live[q + "key_embed.full_layer.2.weight"], live[q + "key_embed.full_layer.3.weight"], live[q + "key_embed.full_layer.3.bias"],
            live[q + "value_embed.full_layer.2.weight"], live[q + "value_embed.full_layer.3.weight"], live[q + "value_embed.full_layer.3.bias"]]
-    out = _AVNetFn.apply(rt, wav, video, *bnp, *[slots[n] for n in _lib.PARAM_NAMES])
+    out = _AVNetFn.apply(rt, wav, video, *bnp, *slot_list)
     return out.view(wav.shape[0], 1, wav.shape[1])
 
 
