@@ -241,6 +241,29 @@ def live_tensors(model):
     return d
 
 
+def _param_versions(model):
+    return tuple(p._version for p in model.parameters())
+
+
+def prepared_slots(rt, device, stash=False):
+    """(live tensors, parameter slots) of the training path.  weights.prepare(train=True) re-derives every weight image from the live
+    parameters with ~400 small torch ops: 6.5 ms of HOST time per step (tools/prep_time.py).  Trainer.step therefore calls this
+    with stash=True right after it has enqueued the optimizer kernel -- the host is ahead of the GPU there, the ops queue behind the
+    update they depend on -- and the next forward picks the result up, provided no parameter was touched in between (tensor
+    versions; the fused optimizer writes through raw pointers and does not bump them)."""
+    model = rt.model
+    key = (_param_versions(model), str(device), torch.is_grad_enabled())
+    cached = getattr(rt, "_prepared_next", None)
+    rt._prepared_next = None
+    if not stash and cached is not None and cached[0] == key:
+        return cached[1], cached[2]
+    live = live_tensors(model)
+    slots = prepare(live, device, train=True)
+    if stash:
+        rt._prepared_next = (key, live, slots)
+    return live, slots
+
+
 def forward_train(rt, wav, mouth):
     """AVNet.forward on the training path (called by nn._Runtime.forward when the model trains / autograd is on)."""
     model = rt.model
@@ -250,8 +273,7 @@ def forward_train(rt, wav, mouth):
         wav = wav[:, 0]
     wav = wav.contiguous()
     rm = model.refinement_module
-    live = live_tensors(model)
-    slots = prepare(live, wav.device, train=True)
+    live, slots = prepared_slots(rt, wav.device)
     # The audio-only part of the forward (encoder, bottleneck, first block pass) is enqueued BEFORE the video block: that block is
     # ~150 eager library launches (more under SyncBatchNorm) and bound by the host, which now works while the GPU is busy.
     B, L, Tv = wav.shape[0], wav.shape[1], mouth.shape[-1]
@@ -488,6 +510,9 @@ class Trainer:
                                                   self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.t, self.clip, 1.0 / self.world,
                                                   self.gnorm.data_ptr(), _stream()), "rtfs_adamw_step")
         mark()
+        rt = getattr(model, "_runtime", None)
+        if rt is not None:  # next step's weight images, derived while the GPU still works through this step's queue
+            prepared_slots(rt, self.flat_p.device, stash=True)
         return loss
 
 

@@ -161,6 +161,25 @@ def pack_video(sd, device, n_head=8):
     return buf
 
 
+_CONSTS = {}
+
+
+def _device_constants(device):
+    """Parameter-independent tables, built once per device.  They used to be rebuilt on the host and copied in every prepare() call:
+    three pageable host -> device copies, each of which makes the host wait for everything queued before it -- in training that
+    is the whole backward of the previous step (tools/prof_train_dp.py: three cudaStreamSynchronize per step, 14 ms each)."""
+    key = str(device)
+    c = _CONSTS.get(key)
+    if c is None:
+        k = torch.arange(256, dtype=torch.float64)
+        c = {"window": torch.hann_window(256, periodic=True, dtype=torch.float32, device=device),
+             "cos": torch.cos(2.0 * math.pi * k / 256).to(torch.float32).to(device),
+             "sin": torch.sin(2.0 * math.pi * k / 256).to(torch.float32).to(device),
+             "mask_perm": torch.stack([torch.arange(128), torch.arange(128) + 128], 1).reshape(-1).to(device)}
+        _CONSTS[key] = c
+    return c
+
+
 def prepare(sd, device, train=False):
     """{reference key: tensor} -> {slot name: tensor}.  train=True: the inputs are the live parameters and every slot is a
     differentiable function of them (reshapes / permutes / straight-through TF32 rounding), so autograd carries the slot
@@ -171,10 +190,8 @@ def prepare(sd, device, train=False):
     else:
         g = lambda k: sd[k].detach().to(device=device, dtype=torch.float32)
     out = {}
-    out["RTFS_P_WINDOW"] = torch.hann_window(256, periodic=True, dtype=torch.float32, device=device)
-    k = torch.arange(256, dtype=torch.float64)
-    out["RTFS_P_COSTAB"] = torch.cos(2.0 * math.pi * k / 256).to(torch.float32).to(device)
-    out["RTFS_P_SINTAB"] = torch.sin(2.0 * math.pi * k / 256).to(torch.float32).to(device)
+    consts = _device_constants(device)
+    out["RTFS_P_WINDOW"], out["RTFS_P_COSTAB"], out["RTFS_P_SINTAB"] = consts["window"], consts["cos"], consts["sin"]
 
     w = g("encoder.conv.full_layer.2.weight")  # (256,2,3,3) [co,ci,i,j] -> k = (i*3+j)*2+ci
     out["RTFS_P_ENC_W"] = torch.cat([w.permute(0, 2, 3, 1).reshape(256, 18), torch.zeros(256, 14, device=device)], 1)
@@ -275,7 +292,7 @@ def prepare(sd, device, train=False):
         out[f"RTFS_P_CAF_{t_slot}"] = g(q + "3.bias") - g(q + "3.running_mean") * inv
 
     out["RTFS_P_MK_A"] = g("mask_generator.mask_generator.0.weight").reshape(1)
-    perm = torch.stack([torch.arange(128), torch.arange(128) + 128], 1).reshape(-1).to(device)
+    perm = consts["mask_perm"]
     out["RTFS_P_MK_W"] = tf32_round(g("mask_generator.mask_generator.1.full_layer.2.weight").reshape(256, 256)[perm])
     out["RTFS_P_MK_B"] = g("mask_generator.mask_generator.1.full_layer.2.bias")[perm].contiguous()
     out["RTFS_P_DEC_W"] = g("decoder.decoder.weight").permute(1, 2, 3, 0).reshape(18, 256).contiguous()
