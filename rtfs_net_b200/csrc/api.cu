@@ -317,8 +317,9 @@ int run_dprnn(const Ctx& c, int which, bool first, const float* g_in, float* g_f
         a.nseq_total = nseq;
         a.n_other = n_other;
         static const bool dbg = env_flag("RTFS_DF_DEBUG");
-        a.yield_sms = c.join_pending ? 1 : 0;  // the forked VP block needs SMs: no persistent CTAs while it is in flight
-        const int tiles = dprnn_fused_dbg_rows(S, nseq, c.join_pending);  // timeline rows; nseq_tile is set by the launcher for the tile size it picks
+        static const bool no_yield = env_flag("RTFS_DF_NO_YIELD");  // A/B: persistent CTAs even while the forked VP block is in flight
+        a.yield_sms = (!no_yield && c.join_pending) ? 1 : 0;  // the forked VP block needs SMs (11.77 vs 11.82 ms per forward)
+        const int tiles = dprnn_fused_dbg_rows(S, nseq, a.yield_sms != 0);  // timeline rows; nseq_tile is set by the launcher for the tile size it picks
         if (dbg) {
             CKN(cudaMalloc(&a.dbg, sizeof(long long) * 32 * tiles));
             CKN(cudaMemset(a.dbg, 0, sizeof(long long) * 32 * tiles));

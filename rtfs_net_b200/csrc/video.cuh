@@ -93,6 +93,52 @@ DEVINL void vp_dwconv(const float* in, int Li, int ldi, float* outp, int Lo, int
     }
 }
 
+// Gateway (dw 1x1 + PReLU) + projection 512 -> 64 (+ folded BN + PReLU): thread = (output channel co, frame phase tq), frames
+// tq, tq + 4, ... , NI of them.  The FMA block is unrolled over the 32 staged input channels x NI frames with every shared-memory
+// address = running row pointer + immediate and no per-element predicate (a frame index past Tv reads the next row / the 64-float
+// pad behind the staging area and lands in an accumulator that is never stored).  It used to be one 32 x 32 block with a predicate
+// and a multiply per address: 13.5 k instructions executed 16 times per warp -- 60 % of the kernel's samples, 35-55 % of them
+// instruction-fetch stalls (ncu: `no_inst`), the body did not fit the instruction cache.
+template <int NI>
+DEVINL void vp_project(const VideoArgs& a, const float* xb, float* stage, float* ybuf) {
+    const int tid = threadIdx.x, Tv = a.Tv;
+    const float* W = a.w;
+    const int* O = a.off.o;
+    const int co = tid & 63, tq = tid >> 6;
+    float acc[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) acc[i] = 0.f;
+    const float ga = __ldg(W + O[VP_GW_A]);
+    for (int c0 = 0; c0 < VP_C; c0 += 32) {
+        // the chunk's 32 weights of this thread's output channel are requested before the staging barrier: 32 independent loads
+        // in flight instead of one L2 round trip per input channel
+        float wv[32];
+#pragma unroll
+        for (int cc = 0; cc < 32; ++cc) wv[cc] = __ldg(W + O[VP_PJ_WT] + (c0 + cc) * VP_N + co);
+        __syncthreads();
+        for (int idx = tid; idx < 32 * Tv; idx += 256) {
+            const int cc = idx / Tv, t = idx - cc * Tv;
+            const float v = fmaf(__ldg(W + O[VP_GW_W] + c0 + cc), __ldg(xb + (c0 + cc) * Tv + t), __ldg(W + O[VP_GW_B] + c0 + cc));
+            stage[cc * Tv + t] = prelu(v, ga);
+        }
+        __syncthreads();
+        const float* r = stage + tq;
+#pragma unroll
+        for (int cc = 0; cc < 32; ++cc) {
+            const float w = wv[cc];
+#pragma unroll
+            for (int i = 0; i < NI; ++i) acc[i] = fmaf(w, r[4 * i], acc[i]);
+            r += Tv;
+        }
+    }
+    const float s = __ldg(W + O[VP_PJ_S] + co), t0 = __ldg(W + O[VP_PJ_T] + co), pa = __ldg(W + O[VP_PJ_A]);
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const int t = tq + 4 * i;
+        if (t < Tv) ybuf[co * Tv + t] = prelu(fmaf(acc[i], s, t0), pa);
+    }
+}
+
 __global__ void __launch_bounds__(256) video_block_kernel(VideoArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, b = blockIdx.x, Tv = a.Tv, SL = a.sumlen;
@@ -110,41 +156,13 @@ __global__ void __launch_bounds__(256) video_block_kernel(VideoArgs a) {
 
     // ---- gateway (dw 1x1 + PReLU) fused into the projection 512 -> 64 (+ BN + PReLU)        tdanet.py:34-49,107-113
     {
-        const int co = tid & 63, tq = tid >> 6;
-        float acc[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-        const float ga = __ldg(W + O[VP_GW_A]);
-        for (int c0 = 0; c0 < VP_C; c0 += 32) {
-            // the chunk's 32 weights of this thread's output channel are requested before the staging barrier: 32 independent loads
-            // in flight instead of one L2 round trip per input channel (ncu: 25 % of the kernel's samples sat on that load)
-            float wv[32];
-#pragma unroll
-            for (int cc = 0; cc < 32; ++cc) wv[cc] = __ldg(W + O[VP_PJ_WT] + (c0 + cc) * VP_N + co);
-            __syncthreads();
-            for (int idx = tid; idx < 32 * Tv; idx += 256) {
-                const int cc = idx / Tv, t = idx - cc * Tv;
-                const float v = fmaf(__ldg(W + O[VP_GW_W] + c0 + cc), __ldg(xb + (c0 + cc) * Tv + t), __ldg(W + O[VP_GW_B] + c0 + cc));
-                stage[cc * Tv + t] = prelu(v, ga);
-            }
-            __syncthreads();
-#pragma unroll
-            for (int cc = 0; cc < 32; ++cc) {
-                const float w = wv[cc];
-                const float* r = stage + cc * Tv;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int t = tq + 4 * i;
-                    if (t < Tv) acc[i] = fmaf(w, r[t], acc[i]);
-                }
-            }
-        }
-        const float s = __ldg(W + O[VP_PJ_S] + co), t0 = __ldg(W + O[VP_PJ_T] + co), pa = __ldg(W + O[VP_PJ_A]);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const int t = tq + 4 * i;
-            if (t < Tv) ybuf[co * Tv + t] = prelu(fmaf(acc[i], s, t0), pa);
-        }
+        const int ni = (Tv + 3) >> 2;  // frames per thread; the unrolled FMA block is instantiated for a few bounds (vp_project)
+        if (ni <= 4) vp_project<4>(a, xb, stage, ybuf);
+        else if (ni <= 7) vp_project<7>(a, xb, stage, ybuf);
+        else if (ni <= 10) vp_project<10>(a, xb, stage, ybuf);
+        else if (ni <= 13) vp_project<13>(a, xb, stage, ybuf);
+        else if (ni <= 19) vp_project<19>(a, xb, stage, ybuf);
+        else vp_project<25>(a, xb, stage, ybuf);
     }
     __syncthreads();
     // ---- down-samplers: ds[0] = bn(dw(y)), ds[i] = bn(dw_s2(ds[i-1]))                         tdanet.py:61-76,113-115
