@@ -85,7 +85,8 @@ def test_bottleneck(model, golden_sd, O):
 
 
 @pytest.mark.parametrize("which,dim", [(0, 4), (1, 3)])
-@pytest.mark.parametrize("Tc,B", [(125, 2), (63, 2), (50, 3), (126, 1)])  # odd tile counts, half-empty last tiles, one utterance
+@pytest.mark.parametrize("Tc,B", [(125, 2), (63, 2), (50, 3), (126, 1), (250, 1)])  # odd tile counts, half-empty last tiles, one
+# utterance; 250 frames: one sequence per 256-position tile on the time path
 def test_dprnn(model, golden_sd, O, which, dim, Tc, B):
     g = torch.Generator().manual_seed(3 + which)
     x = torch.randn(B, 64, Tc, 64, generator=g)
